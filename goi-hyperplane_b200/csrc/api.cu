@@ -1,0 +1,344 @@
+// api.cu -- the extern "C" surface of libgoi_raster.so (include/goi_raster.h): argument validation,
+// scratch-blob carving, stream handling and error reporting around the kernels.
+//
+// Host-side orchestration of the forward replaces CudaRasterizer::Rasterizer::forward
+// (reference cuda_rasterizer/rasterizer_impl.cu:198-344) and the scratch carving replaces
+// GeometryState/ImageState/BinningState::fromChunk (:155-194).
+#include "goi_internal.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace goi {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* where)
+{
+    return fail(GOI_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+}
+#define GOI_CUDA(expr, where) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cuda_fail(e_, where); } while (0)
+
+// debug mode = the reference's CHECK_CUDA (auxiliary.h:166-173): sync + check after every stage
+static int debug_sync(const goi_view* v, cudaStream_t st, const char* where)
+{
+    if (v && v->debug) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cuda_fail(e, where);
+    }
+    return GOI_OK;
+}
+
+template <typename T>
+static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 256)
+{
+    const uintptr_t off = (reinterpret_cast<uintptr_t>(chunk) + alignment - 1) & ~(uintptr_t)(alignment - 1);
+    ptr = reinterpret_cast<T*>(off);
+    chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+GeomState carve_geom(char* base, int P, int S)
+{
+    (void)S;
+    GeomState g{};
+    char* c = base;
+    const size_t Pn = (size_t)(P > 0 ? P : 1);
+    obtain(c, g.meta, 1);
+    obtain(c, g.geo, 2 * Pn);
+    obtain(c, g.rgbd, Pn);
+    obtain(c, g.cov3D, 6 * Pn);
+    obtain(c, g.clamped, Pn);
+    obtain(c, g.tiles_touched, Pn);
+    obtain(c, g.point_offsets, Pn);
+    obtain(c, g.rect, Pn);
+    g.scan_temp_bytes = scan_temp_bytes_for(P);
+    obtain(c, g.scan_temp, g.scan_temp_bytes);
+    g.total_bytes = (size_t)(c - base) + 256;
+    return g;
+}
+ImageState carve_image(char* base, int W, int H)
+{
+    ImageState s{};
+    char* c = base;
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    obtain(c, s.ranges, tiles > 0 ? tiles : 1);
+    obtain(c, s.n_contrib, (size_t)W * H > 0 ? (size_t)W * H : 1);
+    s.total_bytes = (size_t)(c - base) + 256;
+    return s;
+}
+BinningState carve_binning(char* base, int64_t R)
+{
+    BinningState b{};
+    char* c = base;
+    const size_t Rn = (size_t)(R > 0 ? R : 1);
+    obtain(c, b.header, 64);
+    obtain(c, b.keys[0], Rn);
+    obtain(c, b.keys[1], Rn);
+    obtain(c, b.vals[0], Rn);
+    obtain(c, b.vals[1], Rn);
+    b.sort_temp_bytes = sort_temp_bytes_for(R);
+    obtain(c, b.sort_temp, b.sort_temp_bytes);
+    b.total_bytes = (size_t)(c - base) + 256;
+    return b;
+}
+
+static int validate(const goi_view* v, const goi_gaussians* g, bool need_opacity = true)
+{
+    if (!v || !g) return fail(GOI_ERR_INVALID_ARG, "null view/gaussians");
+    if (g->P < 0 || v->width <= 0 || v->height <= 0) return fail(GOI_ERR_INVALID_ARG, "bad P/width/height");
+    if (g->S < 0) return fail(GOI_ERR_INVALID_ARG, "negative channel count");
+    if (g->S > GOI_MAX_SEM) return fail(GOI_ERR_UNSUPPORTED, "S=%d semantic channels > GOI_MAX_SEM=%d", g->S, GOI_MAX_SEM);
+    if ((v->width + TILE - 1) / TILE > 65535 || (v->height + TILE - 1) / TILE > 65535)
+        return fail(GOI_ERR_UNSUPPORTED, "image too large for 16-bit tile coordinates");
+    if (g->P == 0) return GOI_OK;
+    if (!g->means3D || (need_opacity && !g->opacities)) return fail(GOI_ERR_INVALID_ARG, "means3D/opacities are required");
+    if ((g->shs == nullptr) == (g->colors_precomp == nullptr))
+        return fail(GOI_ERR_INVALID_ARG, "Please provide excatly one of either SHs or precomputed colors!");
+    if (((g->scales == nullptr || g->rotations == nullptr) && g->cov3D_precomp == nullptr) ||
+        ((g->scales != nullptr || g->rotations != nullptr) && g->cov3D_precomp != nullptr))
+        return fail(GOI_ERR_INVALID_ARG, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    if (g->S > 0 && !g->semantics) return fail(GOI_ERR_INVALID_ARG, "S > 0 but semantics is NULL");
+    if (g->shs && (g->M < (v->sh_degree + 1) * (v->sh_degree + 1) || v->sh_degree < 0 || v->sh_degree > 3))
+        return fail(GOI_ERR_INVALID_ARG, "sh_degree %d needs %d coefficients, M=%d", v->sh_degree,
+                    (v->sh_degree + 1) * (v->sh_degree + 1), g->M);
+    if (!v->background || !v->viewmatrix || !v->projmatrix || !v->cam_pos)
+        return fail(GOI_ERR_INVALID_ARG, "background/viewmatrix/projmatrix/cam_pos are required device pointers");
+    if (g->rotations && (reinterpret_cast<uintptr_t>(g->rotations) & 15))
+        return fail(GOI_ERR_INVALID_ARG, "rotations must be 16-byte aligned");
+    return GOI_OK;
+}
+
+__global__ void k_count_visible(int P, const int32_t* __restrict__ radii, unsigned long long* out)
+{
+    unsigned long long c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) c += radii[i] > 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+}  // namespace goi
+
+using namespace goi;
+
+extern "C" {
+
+int goi_abi_version(void) { return GOI_ABI_VERSION; }
+const char* goi_last_error(void) { return g_err; }
+
+size_t goi_geom_bytes(int32_t P, int32_t S) { return carve_geom(nullptr, P, S).total_bytes; }
+size_t goi_image_bytes(int32_t width, int32_t height) { return carve_image(nullptr, width, height).total_bytes; }
+size_t goi_binning_bytes(int64_t num_rendered) { return carve_binning(nullptr, num_rendered).total_bytes; }
+
+int goi_forward_prepare(const goi_view* view, const goi_gaussians* g, int32_t* radii, void* geom_buf,
+                        size_t geom_bytes, void* stream, int64_t* num_rendered)
+{
+    int rc = validate(view, g);
+    if (rc != GOI_OK) return rc;
+    if (!num_rendered) return fail(GOI_ERR_INVALID_ARG, "num_rendered is NULL");
+    *num_rendered = 0;
+    if (g->P == 0) return GOI_OK;
+    if (!radii || !geom_buf) return fail(GOI_ERR_INVALID_ARG, "radii/geom_buf are NULL");
+    if (geom_bytes < goi_geom_bytes(g->P, g->S)) return fail(GOI_ERR_WORKSPACE, "geometry buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    GeomState gs = carve_geom((char*)geom_buf, g->P, g->S);
+
+    GOI_CUDA(launch_preprocess_fwd(*view, *g, radii, gs, st), "preprocess");
+    if ((rc = debug_sync(view, st, "preprocess")) != GOI_OK) return rc;
+    GOI_CUDA(run_scan(gs, g->P, st), "prefix sum");
+    // the one host sync of the path (reference: cudaMemcpy at rasterizer_impl.cu:285)
+    Meta host_meta;
+    GOI_CUDA(cudaMemcpyAsync(&host_meta, gs.meta, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "read num_rendered");
+    GOI_CUDA(cudaStreamSynchronize(st), "read num_rendered");
+    if (host_meta.prefilter_violation)
+        return fail(GOI_ERR_INVALID_ARG, "Point is filtered although prefiltered is set. This shouldn't happen!");
+    *num_rendered = (int64_t)host_meta.num_rendered;
+    return GOI_OK;
+}
+
+int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, void* geom_buf,
+                       size_t geom_bytes, void* binning_buf, size_t binning_bytes, void* image_buf,
+                       size_t image_bytes, int64_t num_rendered, void* stream)
+{
+    int rc = validate(view, g);
+    if (rc != GOI_OK) return rc;
+    if (!out || !out->out_color || !out->out_depth || !out->out_alpha || (g->S > 0 && !out->out_semantic))
+        return fail(GOI_ERR_INVALID_ARG, "output image pointers are NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->P == 0) {
+        // reference: nothing is rendered, outputs keep their zero fill (rasterize_points.cu:69-85)
+        const size_t HW = (size_t)view->width * view->height;
+        GOI_CUDA(cudaMemsetAsync(out->out_color, 0, sizeof(float) * 3 * HW, st), "empty");
+        if (g->S > 0) GOI_CUDA(cudaMemsetAsync(out->out_semantic, 0, sizeof(float) * g->S * HW, st), "empty");
+        GOI_CUDA(cudaMemsetAsync(out->out_depth, 0, sizeof(float) * HW, st), "empty");
+        GOI_CUDA(cudaMemsetAsync(out->out_alpha, 0, sizeof(float) * HW, st), "empty");
+        return GOI_OK;
+    }
+    if (!geom_buf || !image_buf || (num_rendered > 0 && !binning_buf)) return fail(GOI_ERR_INVALID_ARG, "scratch blobs are NULL");
+    if (geom_bytes < goi_geom_bytes(g->P, g->S)) return fail(GOI_ERR_WORKSPACE, "geometry buffer too small");
+    if (image_bytes < goi_image_bytes(view->width, view->height)) return fail(GOI_ERR_WORKSPACE, "image buffer too small");
+    if (binning_bytes < goi_binning_bytes(num_rendered)) return fail(GOI_ERR_WORKSPACE, "binning buffer too small");
+    if (num_rendered >= (int64_t)1 << 31) return fail(GOI_ERR_UNSUPPORTED, "more than 2^31 instances");
+
+    GeomState gs = carve_geom((char*)geom_buf, g->P, g->S);
+    ImageState is = carve_image((char*)image_buf, view->width, view->height);
+    BinningState bs = carve_binning((char*)binning_buf, num_rendered);
+    int selector = 0;
+    GOI_CUDA(run_binning(*view, g->P, out->radii, gs, bs, is, num_rendered, &selector, st), "binning");
+    if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
+    GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], is, st), "composite forward");
+    return debug_sync(view, st, "composite forward");
+}
+
+int goi_forward(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
+                goi_alloc_fn geometry_buffer, void* geometry_user, goi_alloc_fn binning_buffer, void* binning_user,
+                goi_alloc_fn image_buffer, void* image_user, void* stream, int64_t* num_rendered)
+{
+    int rc = validate(view, g);
+    if (rc != GOI_OK) return rc;
+    if (!geometry_buffer || !binning_buffer || !image_buffer || !out || !num_rendered)
+        return fail(GOI_ERR_INVALID_ARG, "allocator callbacks / out / num_rendered are NULL");
+    const size_t gb = goi_geom_bytes(g->P, g->S);
+    void* geom = geometry_buffer(geometry_user, gb);
+    const size_t ib = goi_image_bytes(view->width, view->height);
+    void* img = image_buffer(image_user, ib);
+    if (!geom || !img) return fail(GOI_ERR_WORKSPACE, "scratch allocator returned NULL");
+    rc = goi_forward_prepare(view, g, out->radii, geom, gb, stream, num_rendered);
+    if (rc != GOI_OK) return rc;
+    const size_t bb = goi_binning_bytes(*num_rendered);
+    void* bin = binning_buffer(binning_user, bb);
+    if (!bin) return fail(GOI_ERR_WORKSPACE, "binning allocator returned NULL");
+    return goi_forward_render(view, g, out, geom, gb, bin, bb, img, ib, *num_rendered, stream);
+}
+
+int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rendered, const goi_bwd_in* in,
+                 const goi_bwd_out* out, void* geom_buf, void* binning_buf, void* image_buf, void* stream)
+{
+    int rc = validate(view, g, /*need_opacity=*/false);   // opacity lives in the geometry records
+    if (rc != GOI_OK) return rc;
+    if (!in || !out) return fail(GOI_ERR_INVALID_ARG, "null in/out");
+    if (g->P == 0) return GOI_OK;
+    if (!in->out_alpha || !in->radii) return fail(GOI_ERR_INVALID_ARG, "out_alpha/radii (forward outputs) are required");
+    if (!out->dL_dmean2D || !out->dL_dconic || !out->dL_dopacity || !out->dL_dcolor || !out->dL_ddepth ||
+        !out->dL_dmean3D || (g->S > 0 && !out->dL_dsemantic))
+        return fail(GOI_ERR_INVALID_ARG, "required gradient outputs are NULL");
+    if (g->shs && !out->dL_dsh) return fail(GOI_ERR_INVALID_ARG, "dL_dsh is NULL but SHs were given");
+    if (g->scales && (!out->dL_dscale || !out->dL_drot || !out->dL_dcov3D))
+        return fail(GOI_ERR_INVALID_ARG, "dL_dscale/dL_drot/dL_dcov3D are NULL but scales were given");
+    if (!geom_buf || !image_buf || (num_rendered > 0 && !binning_buf)) return fail(GOI_ERR_INVALID_ARG, "scratch blobs are NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = (size_t)g->P;
+
+    GeomState gs = carve_geom((char*)geom_buf, g->P, g->S);
+    ImageState is = carve_image((char*)image_buf, view->width, view->height);
+    BinningState bs = carve_binning((char*)binning_buf, num_rendered);
+
+    // accumulators of the composite backward (everything else is fully written by k_preprocess_bwd)
+    GOI_CUDA(cudaMemsetAsync(out->dL_dmean2D, 0, sizeof(float) * 3 * P, st), "zero grads");
+    GOI_CUDA(cudaMemsetAsync(out->dL_dconic, 0, sizeof(float) * 4 * P, st), "zero grads");
+    GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
+    GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
+    GOI_CUDA(cudaMemsetAsync(out->dL_ddepth, 0, sizeof(float) * P, st), "zero grads");
+    if (g->S > 0) GOI_CUDA(cudaMemsetAsync(out->dL_dsemantic, 0, sizeof(float) * (size_t)g->S * P, st), "zero grads");
+
+    if (num_rendered > 0) {
+        GOI_CUDA(launch_composite_bwd(*view, *g, *in, *out, gs, bs.vals[0], is, st), "composite backward");
+        if ((rc = debug_sync(view, st, "composite backward")) != GOI_OK) return rc;
+    }
+    GOI_CUDA(launch_preprocess_bwd(*view, *g, *in, *out, gs, st), "preprocess backward");
+    return debug_sync(view, st, "preprocess backward");
+}
+
+int goi_trace(const goi_view* view, const goi_gaussians* g, const float* img_sem, float* out_color, float* gau_sem,
+              int32_t* num_gsem, int32_t* radii, int32_t count_per_channel,
+              goi_alloc_fn geometry_buffer, void* geometry_user, goi_alloc_fn binning_buffer, void* binning_user,
+              goi_alloc_fn image_buffer, void* image_user, void* stream, int64_t* num_rendered)
+{
+    goi_gaussians gg = *g;
+    const int S = g->S;
+    gg.semantics = nullptr;         // trace has no per-Gaussian semantic input (img_sem is an image)
+    gg.S = 0;
+    int rc = validate(view, &gg);
+    if (rc != GOI_OK) return rc;
+    if (S < 0 || (S > 0 && !img_sem)) return fail(GOI_ERR_INVALID_ARG, "img_sem is NULL");
+    if (!out_color || !gau_sem || !num_gsem || !radii || !num_rendered) return fail(GOI_ERR_INVALID_ARG, "null outputs");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t HW = (size_t)view->width * view->height;
+    GOI_CUDA(cudaMemsetAsync(gau_sem, 0, sizeof(float) * (size_t)g->P * (S > 0 ? S : 0), st), "zero gau_sem");
+    GOI_CUDA(cudaMemsetAsync(num_gsem, 0, sizeof(int32_t) * (size_t)g->P, st), "zero num_gsem");
+    *num_rendered = 0;
+    if (g->P == 0) { GOI_CUDA(cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * HW, st), "empty"); return GOI_OK; }
+
+    const size_t gb = goi_geom_bytes(g->P, 0);
+    void* geom = geometry_buffer(geometry_user, gb);
+    const size_t ib = goi_image_bytes(view->width, view->height);
+    void* img = image_buffer(image_user, ib);
+    if (!geom || !img) return fail(GOI_ERR_WORKSPACE, "scratch allocator returned NULL");
+    rc = goi_forward_prepare(view, &gg, radii, geom, gb, stream, num_rendered);
+    if (rc != GOI_OK) return rc;
+    const size_t bb = goi_binning_bytes(*num_rendered);
+    void* bin = binning_buffer(binning_user, bb);
+    if (!bin) return fail(GOI_ERR_WORKSPACE, "binning allocator returned NULL");
+    GeomState gs = carve_geom((char*)geom, g->P, 0);
+    ImageState is = carve_image((char*)img, view->width, view->height);
+    BinningState bs = carve_binning((char*)bin, *num_rendered);
+    int selector = 0;
+    GOI_CUDA(run_binning(*view, g->P, radii, gs, bs, is, *num_rendered, &selector, st), "binning");
+    gg.S = S;
+    GOI_CUDA(launch_trace(*view, gg, img_sem, out_color, gau_sem, num_gsem, count_per_channel, gs, bs.vals[0], is, st), "trace");
+    return debug_sync(view, st, "trace");
+}
+
+int goi_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream)
+{
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GOI_ERR_INVALID_ARG, "null pointers");
+    GOI_CUDA(launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream), "markVisible");
+    return GOI_OK;
+}
+
+int goi_mask(const goi_mask_args* a, void* stream)
+{
+    if (!a) return fail(GOI_ERR_INVALID_ARG, "null args");
+    if (a->N < 0 || a->S <= 0 || a->K <= 0 || a->D <= 0) return fail(GOI_ERR_INVALID_ARG, "bad N/S/K/D");
+    if (a->S > GOI_MAX_SEM) return fail(GOI_ERR_UNSUPPORTED, "S=%d > GOI_MAX_SEM", a->S);
+    if (a->mode != GOI_MASK_APE && a->mode != GOI_MASK_OSH) return fail(GOI_ERR_INVALID_ARG, "bad mode");
+    if (!a->x || !a->mlp_weight || !a->lut || !a->hyperplane_w || !a->sim_table || !a->sim)
+        return fail(GOI_ERR_INVALID_ARG, "null pointers");
+    const size_t smem = (size_t)a->K * sem_groups(a->S) * 16 + 2 * (size_t)a->K * 4;
+    if (smem > 200 * 1024) return fail(GOI_ERR_UNSUPPORTED, "codebook projection (K=%d, S=%d) does not fit shared memory", a->K, a->S);
+    GOI_CUDA(launch_mask(*a, (cudaStream_t)stream), "mask");
+    return GOI_OK;
+}
+
+int goi_read_stats(const goi_view* view, const goi_gaussians* g, const void* geom_buf, const int32_t* radii,
+                   void* stream, goi_stats* stats)
+{
+    if (!view || !g || !geom_buf || !radii || !stats) return fail(GOI_ERR_INVALID_ARG, "null pointers");
+    cudaStream_t st = (cudaStream_t)stream;
+    GeomState gs = carve_geom((char*)geom_buf, g->P, g->S);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(&gs.meta->reserved[2]);
+    GOI_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st), "stats");
+    if (g->P > 0) k_count_visible<<<256, 256, 0, st>>>(g->P, radii, counter);
+    Meta host_meta;
+    GOI_CUDA(cudaMemcpyAsync(&host_meta, gs.meta, sizeof(Meta), cudaMemcpyDeviceToHost, st), "stats");
+    GOI_CUDA(cudaStreamSynchronize(st), "stats");
+    stats->num_rendered = host_meta.num_rendered;
+    unsigned long long vis;
+    memcpy(&vis, &host_meta.reserved[2], sizeof(vis));
+    stats->num_visible = (int64_t)vis;
+    stats->tiles_x = (view->width + TILE - 1) / TILE;
+    stats->tiles_y = (view->height + TILE - 1) / TILE;
+    return GOI_OK;
+}
+
+}  // extern "C"

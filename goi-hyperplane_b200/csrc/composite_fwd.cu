@@ -1,0 +1,215 @@
+// composite_fwd.cu -- front-to-back alpha composite of RGB + S semantic channels + depth + alpha.
+//
+// Replaces renderCUDA<3,S> (forward), reference cuda_rasterizer/forward.cu:261-386, and
+// traceCUDA<3,S> (:422-551).  Numerical contract, per pixel, instances in
+// list order:
+//     d = xy - pix;  power = -0.5(A dx^2 + C dy^2) - B dx dy;   power > 0        -> skip
+//     alpha = min(0.99, o * expf(power));                        alpha < 1/255    -> skip
+//     test_T = T (1 - alpha);                                    test_T < 1e-4    -> pixel done
+//     acc += payload * alpha * T;  T = test_T;  last = list index (1-based)
+// power/alpha/test_T are evaluated with the reference's expression order and precise expf so the
+// three step functions take the same branch.
+//
+// B200 design (what differs from the reference kernel):
+//   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block (compact footprint =>
+//     more whole-warp rejects than the reference's 16x2 rows);
+//   * instances are staged 128 at a time into shared memory with cp.async (LDGSTS), double
+//     buffered, INCLUDING the payload row (rgb, depth, S semantic floats, float4-vectorised):
+//     the reference re-reads S+4 scalars from global memory per contributing pair (:360-364);
+//   * per Gaussian record is two float4 (xy+conic, conic.z+opacity+power_cut) -> two broadcast
+//     LDS.128 per pair instead of three scattered arrays;
+//   * power_cut (precomputed -ln(255 o) - margin) rejects provably non-contributing pairs
+//     before the expf; a warp vote skips the payload FMAs when no lane blends;
+//   * S is a run-time value: kernels are instantiated per float4-group count (0..16 groups).
+// HBM roofline: algorithmic bytes per instance = 4 (id) + 32 (geo) + 16 (rgbd) + 4S (sem);
+// per pixel = 4(S+5) + 4 written.
+#include "goi_internal.cuh"
+
+namespace goi {
+
+template <int NS4, int BATCH, bool TRACE>
+__global__ void __launch_bounds__(COMPOSITE_THREADS)
+k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+                const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
+                int S, int sem_vec, const float* __restrict__ bg,
+                float* __restrict__ out_color, float* __restrict__ out_sem, float* __restrict__ out_depth,
+                float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
+                // trace mode only:
+                const float* __restrict__ img_sem, float* __restrict__ gau_sem, int32_t* __restrict__ num_gsem,
+                int count_per_channel)
+{
+    constexpr int ROW = 1 + NS4;                       // float4 per payload row: (r,g,b,depth) + semantics
+    extern __shared__ float4 smem[];
+    float4* s_geo = smem;                              // [2][BATCH][2]
+    float4* s_pay = smem + 2 * BATCH * 2;              // [2][BATCH][ROW]
+    __shared__ int s_id[2][BATCH];                     // Gaussian ids (trace mode scatters by id)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % gx, ty = tile / gx;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+
+    const uint2 range = ranges[tile];
+    const int n = (int)(range.y - range.x);
+    const int nb = (n + BATCH - 1) / BATCH;
+
+    if (!TRACE && NS4 > 0 && 4 * NS4 != S) {           // padded semantic lanes must read as zero
+        for (int i = tid; i < 2 * BATCH * ROW; i += COMPOSITE_THREADS) s_pay[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+    }
+
+    auto stage = [&](int b) {
+        const int buf = b & 1;
+        const int base = (int)range.x + b * BATCH;
+        const int cnt = min(BATCH, n - b * BATCH);
+        constexpr int PARTS = (!TRACE && NS4 > 0) ? 2 : 1;
+        for (int wi = tid; wi < cnt * PARTS; wi += COMPOSITE_THREADS) {
+            const int j = wi / PARTS, part = wi % PARTS;
+            const uint32_t id = point_list[base + j];
+            if (part == 0) {
+                cp_async16(&s_geo[(buf * BATCH + j) * 2], &geo[2 * (size_t)id]);
+                cp_async16(&s_geo[(buf * BATCH + j) * 2 + 1], &geo[2 * (size_t)id + 1]);
+                cp_async16(&s_pay[(buf * BATCH + j) * ROW], &rgbd[id]);
+                if (TRACE) s_id[buf][j] = (int)id;
+            } else {
+                float4* dst = &s_pay[(buf * BATCH + j) * ROW + 1];
+                const float* src = sem + (size_t)id * S;
+                if (sem_vec) {
+                    for (int k = 0; k < (S >> 2); ++k) cp_async16(dst + k, src + 4 * k);
+                } else {
+                    for (int c = 0; c < S; ++c) cp_async4(reinterpret_cast<float*>(dst) + c, src + c);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dacc = 0.f;
+    float Cs[NS4 > 0 ? 4 * NS4 : 1];
+#pragma unroll
+    for (int i = 0; i < (NS4 > 0 ? 4 * NS4 : 1); ++i) Cs[i] = 0.f;
+    bool done = !inside;
+
+    if (nb > 0) stage(0);
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait_all();
+        if (__syncthreads_count(!done) == 0) break;     // batch b landed; batch b-1 fully consumed
+        if (b + 1 < nb) stage(b + 1);
+
+        const int buf = b & 1;
+        const int cnt = min(BATCH, n - b * BATCH);
+        const float4* sg = s_geo + buf * BATCH * 2;
+        const float4* sp = s_pay + buf * BATCH * ROW;
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int j = 0; j < cnt; ++j) {
+            const float4 g0 = sg[2 * j];
+            const float4 g1 = sg[2 * j + 1];
+            const float dx = g0.x - pxf, dy = g0.y - pyf;
+            const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+            bool hit = !done && !(power > 0.0f) && !(power < g1.z);
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            float alpha = 0.f, test_T = 0.f;
+            if (hit) {
+                alpha = fminf(0.99f, g1.y * expf(power));
+                if (alpha < 1.0f / 255.0f) hit = false;
+                else {
+                    test_T = T * (1 - alpha);
+                    if (test_T < 0.0001f) { done = true; hit = false; }
+                }
+            }
+            if (__any_sync(0xffffffffu, hit)) {
+                const float w = hit ? alpha * T : 0.f;
+                const float4 p0 = sp[j * ROW];
+                C0 = fmaf(p0.x, w, C0); C1 = fmaf(p0.y, w, C1); C2 = fmaf(p0.z, w, C2);
+                if (!TRACE) {
+                    Dacc = fmaf(p0.w, w, Dacc);
+#pragma unroll
+                    for (int k = 0; k < NS4; ++k) {
+                        const float4 s4 = sp[j * ROW + 1 + k];
+                        Cs[4 * k + 0] = fmaf(s4.x, w, Cs[4 * k + 0]);
+                        Cs[4 * k + 1] = fmaf(s4.y, w, Cs[4 * k + 1]);
+                        Cs[4 * k + 2] = fmaf(s4.z, w, Cs[4 * k + 2]);
+                        Cs[4 * k + 3] = fmaf(s4.w, w, Cs[4 * k + 3]);
+                    }
+                } else if (hit && alpha > 0.005) {
+                    // traceCUDA, forward.cu:521-526, with atomics instead of the reference's racy `+=`
+                    const int id = s_id[buf][j];
+                    for (int ch = 0; ch < S; ++ch) atomicAdd(&gau_sem[(size_t)id * S + ch], img_sem[ch * HW + pix]);
+                    atomicAdd(&num_gsem[id], count_per_channel ? S : 1);
+                }
+                if (hit) { T = test_T; last_contributor = (uint32_t)(b * BATCH + j + 1); }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+
+    if (inside) {
+        n_contrib[pix] = last_contributor;
+        out_color[pix] = C0 + T * bg[0];
+        out_color[HW + pix] = C1 + T * bg[1];
+        out_color[2 * HW + pix] = C2 + T * bg[2];
+        if (!TRACE) {
+#pragma unroll
+            for (int ch = 0; ch < 4 * NS4; ++ch)
+                if (ch < S) out_sem[ch * HW + pix] = Cs[ch];
+            out_alpha[pix] = 1 - T;
+            out_depth[pix] = Dacc;
+        }
+    }
+}
+
+template <int NS4, bool TRACE>
+static cudaError_t launch_fwd_t(const goi_view& v, const goi_gaussians& g, const GeomState& gs,
+                                const uint32_t* point_list, const ImageState& is, float* out_color,
+                                float* out_sem, float* out_depth, float* out_alpha, const float* img_sem,
+                                float* gau_sem, int32_t* num_gsem, int count_per_channel, cudaStream_t st)
+{
+    constexpr int BATCH = 128;
+    constexpr int ROW = 1 + NS4;
+    const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
+    const size_t smem = (size_t)2 * BATCH * (2 + ROW) * sizeof(float4);
+    auto kern = k_composite_fwd<NS4, BATCH, TRACE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
+    kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(is.ranges, point_list, v.width, v.height, gx, gs.geo, gs.rgbd,
+                                                   g.semantics, g.S, sem_vec, v.background, out_color, out_sem,
+                                                   out_depth, out_alpha, is.n_contrib, img_sem, gau_sem, num_gsem,
+                                                   count_per_channel);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
+                                 const GeomState& gs, const uint32_t* point_list, const ImageState& is,
+                                 cudaStream_t st)
+{
+#define GOI_FWD(N) return launch_fwd_t<N, false>(v, g, gs, point_list, is, out.out_color, out.out_semantic, \
+                                                  out.out_depth, out.out_alpha, nullptr, nullptr, nullptr, 0, st)
+    switch (sem_groups(g.S)) {
+        case 0: GOI_FWD(0);
+        case 1: GOI_FWD(1);
+        case 2: GOI_FWD(2);
+        case 3: GOI_FWD(3);
+        case 4: GOI_FWD(4);
+        case 8: GOI_FWD(8);
+        default: GOI_FWD(16);
+    }
+#undef GOI_FWD
+}
+
+cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float* img_sem, float* out_color,
+                         float* gau_sem, int32_t* num_gsem, int count_per_channel, const GeomState& gs,
+                         const uint32_t* point_list, const ImageState& is, cudaStream_t st)
+{
+    return launch_fwd_t<0, true>(v, g, gs, point_list, is, out_color, nullptr, nullptr, nullptr, img_sem, gau_sem,
+                                 num_gsem, count_per_channel, st);
+}
+
+}  // namespace goi

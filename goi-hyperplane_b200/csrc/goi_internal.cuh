@@ -1,0 +1,109 @@
+// goi_internal.cuh -- private declarations shared by the kernels of libgoi_raster.so.
+// Nothing here is part of the C ABI (include/goi_raster.h); layouts may change per build.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/goi_raster.h"
+
+namespace goi {
+
+constexpr int TILE = GOI_TILE;            // 16x16 pixel tiles (reference: BLOCK_X/BLOCK_Y, config.h:16-17)
+constexpr int TILE_PIX = TILE * TILE;
+constexpr int COMPOSITE_THREADS = 256;    // one thread per pixel of a tile, 8 warps of 8x4 pixels
+
+// Device-side counters written by the kernels and read back by the host where needed.
+struct Meta {
+    uint32_t num_rendered;       // R, from the prefix sum
+    uint32_t prefilter_violation;
+    uint32_t reserved[62];
+};
+
+// Geometry scratch ("geomBuffer"): per-Gaussian records produced by preprocess and
+// consumed by binning, both composites and the per-Gaussian backward.
+//   geo[2i+0] = (mean2D.x, mean2D.y, conic.x, conic.y)
+//   geo[2i+1] = (conic.z, opacity, power_cut, 0)
+//   rgbd[i]   = (r, g, b, view-space depth)        -- the non-semantic payload of an instance
+//   rect[i]   = (minx | miny<<16, maxx | maxy<<16) -- tile rectangle of getRect()
+struct GeomState {
+    float4*   geo;
+    float4*   rgbd;
+    float*    cov3D;             // [P,6]
+    uint8_t*  clamped;           // [P] bit c set = colour channel c was clamped at 0
+    uint32_t* tiles_touched;     // [P]
+    uint32_t* point_offsets;     // [P] inclusive prefix sum
+    uint2*    rect;              // [P]
+    Meta*     meta;
+    char*     scan_temp;
+    size_t    scan_temp_bytes;
+    size_t    total_bytes;
+};
+struct ImageState {
+    uint2*    ranges;            // [tiles]  [start,end) into point_list
+    uint32_t* n_contrib;         // [H*W]    1-based index of the last blended list entry
+    size_t    total_bytes;
+};
+struct BinningState {
+    uint64_t* keys[2];           // double buffer: tile<<32 | depth bits
+    uint32_t* vals[2];           // double buffer: Gaussian index
+    uint32_t* selector;          // (device) unused; host keeps the selector in the header word below
+    char*     sort_temp;
+    size_t    sort_temp_bytes;
+    uint32_t* header;            // [64] word 0 = which half of the double buffers holds the sorted list
+    size_t    total_bytes;
+};
+
+GeomState    carve_geom(char* base, int P, int S);
+ImageState   carve_image(char* base, int W, int H);
+BinningState carve_binning(char* base, int64_t R);
+
+inline int sem_groups(int S) {           // float4 groups the composite kernels are instantiated for
+    if (S <= 0) return 0;
+    if (S <= 4) return 1;
+    if (S <= 8) return 2;
+    if (S <= 12) return 3;
+    if (S <= 16) return 4;
+    if (S <= 32) return 8;
+    return 16;
+}
+
+// ---- launchers (each returns cudaGetLastError() of its launches) -----------------------------
+cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int32_t* radii,
+                                  const GeomState& gs, cudaStream_t st);
+cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st);
+cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const GeomState& gs,
+                        const BinningState& bs, const ImageState& is, int64_t R, int* selector_out,
+                        cudaStream_t st);
+size_t scan_temp_bytes_for(int P);
+size_t sort_temp_bytes_for(int64_t R);
+
+cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
+                                 const GeomState& gs, const uint32_t* point_list, const ImageState& is,
+                                 cudaStream_t st);
+cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
+                                 const goi_bwd_out& out, const GeomState& gs, const uint32_t* point_list,
+                                 const ImageState& is, cudaStream_t st);
+cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
+                                  const goi_bwd_out& out, const GeomState& gs, cudaStream_t st);
+cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float* img_sem, float* out_color,
+                         float* gau_sem, int32_t* num_gsem, int count_per_channel, const GeomState& gs,
+                         const uint32_t* point_list, const ImageState& is, cudaStream_t st);
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                                cudaStream_t st);
+cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st);
+
+// ---- small device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
+#endif
+
+}  // namespace goi

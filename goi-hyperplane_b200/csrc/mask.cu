@@ -1,0 +1,158 @@
+// mask.cu -- fused open-vocabulary mask: semantic features -> codebook row -> hyperplane test.
+//
+// Replaces the torch expression chain of GUI.compute_similarity (reference gui/main.py:363-385):
+//     dec  = Linear(S -> K)(x)                      scene/semantic_model.py:45-50, train.py:64
+//     idx  = softmax(dec * 10).argmax(-1)           gui/main.py:366
+//     f    = LUT[idx];  f = f / ||f||               :367-371
+//     APE: sim = sigmoid(clamp(f.w / exp(log_scale), +-50000) + 2)
+//                                                   ext/vision_language_align.py:109-122, gui/main.py:113-117
+//     OSH: sim = sigmoid(Linear(256 -> 1)(f / 0.3438))          networks.py:58-59, gui/main.py:374-377
+//     bg   = sim < thresh;  sim[bg] = 0             gui/main.py:381-384
+// The reference materialises [N,K] logits + softmax and two [N,D] feature tensors (about 7 GB of
+// temporaries at 1.6 Mpx).  Everything after the argmax depends only on idx, so the K-entry sim table
+// is computed once (k_mask_table, K blocks) and the per-element kernel does the S->K projection in
+// registers, tracks the arg-max (first maximum wins, like torch.argmax), and does one table lookup:
+// 4S bytes in, 4 + 1 (+4) bytes out per element.  softmax(10 x) is strictly monotone in x, so its
+// argmax is the argmax of the logits (ties at float resolution are the documented exception).
+#include "goi_internal.cuh"
+
+namespace goi {
+
+__global__ void __launch_bounds__(128) k_mask_table(int K, int D, int mode, const float* __restrict__ lut,
+                                                    const float* __restrict__ w, float bias, float log_scale,
+                                                    float* __restrict__ sim_table)
+{
+    const int k = blockIdx.x;
+    const float* f = lut + (size_t)k * D;
+    float n2 = 0.f, dt = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { const float x = f[d]; n2 = fmaf(x, x, n2); dt = fmaf(x, w[d], dt); }
+    __shared__ float s_n2[4], s_dt[4];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+        dt += __shfl_xor_sync(0xffffffffu, dt, off);
+    }
+    if ((threadIdx.x & 31) == 0) { s_n2[threadIdx.x >> 5] = n2; s_dt[threadIdx.x >> 5] = dt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        n2 = s_n2[0] + s_n2[1] + s_n2[2] + s_n2[3];
+        dt = s_dt[0] + s_dt[1] + s_dt[2] + s_dt[3];
+        const float nrm = sqrtf(n2);
+        float logit;
+        if (mode == GOI_MASK_APE) {
+            logit = (dt / nrm) / expf(log_scale);
+            logit = fminf(fmaxf(logit, -50000.f), 50000.f) + 2.f;
+        } else {
+            logit = (dt / nrm) / 0.3438f + bias;
+        }
+        sim_table[k] = 1.0f / (1.0f + expf(-logit));
+    }
+}
+
+template <int NS4, int PPT>
+__global__ void __launch_bounds__(256) k_mask_apply(int64_t N, int S, int K, int64_t stride_n, int64_t stride_c,
+                                                    const float* __restrict__ x, const float* __restrict__ mlp_w,
+                                                    const float* __restrict__ mlp_b,
+                                                    const float* __restrict__ sim_table, float thresh,
+                                                    float* __restrict__ sim, uint8_t* __restrict__ bg_mask,
+                                                    int32_t* __restrict__ idx_out)
+{
+    constexpr int SP = 4 * NS4;                         // padded channel count
+    extern __shared__ float4 smem_m[];
+    float4* s_w = smem_m;                               // [K][NS4]
+    float* s_b = reinterpret_cast<float*>(smem_m + (size_t)K * NS4);   // [K]
+    float* s_tab = s_b + K;                             // [K]
+    for (int i = threadIdx.x; i < K * SP; i += blockDim.x) {
+        const int k = i / SP, c = i % SP;
+        reinterpret_cast<float*>(s_w)[i] = c < S ? mlp_w[(size_t)k * S + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { s_b[i] = mlp_b ? mlp_b[i] : 0.f; s_tab[i] = sim_table[i]; }
+    __syncthreads();
+
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x) * PPT; base < N; base += (int64_t)gridDim.x * blockDim.x * PPT) {
+        float xv[PPT][SP];
+        int64_t nidx[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            nidx[p] = base + (int64_t)p * blockDim.x + threadIdx.x;   // consecutive threads -> consecutive elements
+#pragma unroll
+            for (int c = 0; c < SP; ++c)
+                xv[p][c] = (c < S && nidx[p] < N) ? x[nidx[p] * stride_n + c * stride_c] : 0.f;
+        }
+        float best[PPT];
+        int bi[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) { best[p] = -INFINITY; bi[p] = 0; }
+        for (int k = 0; k < K; ++k) {
+            float a[PPT];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) a[p] = 0.f;
+#pragma unroll
+            for (int q = 0; q < NS4; ++q) {
+                const float4 w4 = s_w[k * NS4 + q];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    a[p] = fmaf(xv[p][4 * q + 0], w4.x, a[p]);
+                    a[p] = fmaf(xv[p][4 * q + 1], w4.y, a[p]);
+                    a[p] = fmaf(xv[p][4 * q + 2], w4.z, a[p]);
+                    a[p] = fmaf(xv[p][4 * q + 3], w4.w, a[p]);
+                }
+            }
+            const float bk = s_b[k];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                const float v = a[p] + bk;
+                if (v > best[p]) { best[p] = v; bi[p] = k; }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            if (nidx[p] < N) {
+                const float s = s_tab[bi[p]];
+                const bool bg = s < thresh;
+                sim[nidx[p]] = bg ? 0.f : s;
+                if (bg_mask) bg_mask[nidx[p]] = bg ? 1 : 0;
+                if (idx_out) idx_out[nidx[p]] = bi[p];
+            }
+        }
+    }
+}
+
+template <int NS4, int PPT>
+static cudaError_t launch_mask_t(const goi_mask_args& a, cudaStream_t st)
+{
+    auto kern = k_mask_apply<NS4, PPT>;
+    const size_t smem = (size_t)a.K * NS4 * sizeof(float4) + 2 * (size_t)a.K * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t per_block = 256 * PPT;
+    int64_t blocks = (a.N + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sms * 8;              // grid-stride: a few resident CTAs per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, 256, smem, st>>>(a.N, a.S, a.K, a.stride_n, a.stride_c, a.x, a.mlp_weight, a.mlp_bias,
+                                              a.sim_table, a.thresh, a.sim, a.bg_mask, a.idx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
+{
+    k_mask_table<<<a.K, 128, 0, st>>>(a.K, a.D, a.mode, a.lut, a.hyperplane_w, a.hyperplane_b, a.log_scale, a.sim_table);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (a.N <= 0) return cudaSuccess;
+    switch (sem_groups(a.S)) {
+        case 0: return cudaErrorInvalidValue;
+        case 1: return launch_mask_t<1, 4>(a, st);
+        case 2: return launch_mask_t<2, 4>(a, st);
+        case 3: return launch_mask_t<3, 2>(a, st);
+        case 4: return launch_mask_t<4, 2>(a, st);
+        case 8: return launch_mask_t<8, 1>(a, st);
+        default: return launch_mask_t<16, 1>(a, st);
+    }
+}
+
+}  // namespace goi

@@ -1,0 +1,202 @@
+"""Drop-in replacement for the reference's ``diff_gaussian_rasterization`` Python package
+(/root/reference/submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py).
+
+Same public names, argument order, return tuples and error behaviour:
+
+* ``GaussianRasterizationSettings``            reference :246-258
+* ``GaussianRasterizer(nn.Module)`` with ``forward`` / ``markVisible`` / ``trace``   :260-349
+* ``rasterize_gaussians`` / ``trace_gaussians``  :21-69
+* ``_RasterizeGaussians(autograd.Function)``     :71-244 (saves the same 12 tensors, returns the
+  gradients in the same order, keeps the debug snapshot dumps)
+
+so ``gaussian_renderer.render`` (reference gaussian_renderer/__init__.py:14,86-95), ``train.py``,
+``render.py`` and ``gui/gs_renderer.py`` import and call it unchanged.  Differences, all widening:
+the semantic channel count is ``semantics.shape[1]`` at run time (the reference hard-codes
+SEM_CHANNELS=10, cuda_rasterizer/config.h:18); ``semantics=None`` means S=0; kernels run on
+torch's current stream under a device guard.  All compute happens in libgoi_raster.so (``_C.py``).
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _C
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+def trace_gaussians(means3D, means2D, sh, colors_precomp, img_sem, opacities, scales, rotations, cov3Ds_precomp,
+                    raster_settings):
+    return _RasterizeGaussians.trace(means3D, means2D, sh, colors_precomp, img_sem, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        # Restructure arguments the way the C++/CUDA side expects them (reference :86-107)
+        args = (raster_settings.bg, means3D, colors_precomp, semantics, opacities, scales, rotations,
+                raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
+                raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy,
+                raster_settings.image_height, raster_settings.image_width, sh, raster_settings.sh_degree,
+                raster_settings.campos, raster_settings.prefiltered, raster_settings.debug)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
+            try:
+                (num_rendered, color, semant, depth, alpha, radii, geomBuffer, binningBuffer,
+                 imgBuffer) = _C.rasterize_gaussians(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            (num_rendered, color, semant, depth, alpha, radii, geomBuffer, binningBuffer,
+             imgBuffer) = _C.rasterize_gaussians(*args)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.opacity_shape = opacities.shape
+        ctx.save_for_backward(colors_precomp, semantics, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
+                              geomBuffer, binningBuffer, imgBuffer, alpha)
+        ctx.mark_non_differentiable(radii)
+        return color, semant, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_sem, grad_out_radii, grad_depth, grad_alpha):
+        num_rendered = ctx.num_rendered
+        raster_settings = ctx.raster_settings
+        (colors_precomp, semantics, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+         binningBuffer, imgBuffer, alpha) = ctx.saved_tensors
+        args = (raster_settings.bg, means3D, radii, colors_precomp, semantics, scales, rotations,
+                raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
+                raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy, grad_out_color,
+                grad_out_sem, grad_depth, grad_alpha, sh, raster_settings.sh_degree, raster_settings.campos,
+                geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, raster_settings.debug)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                (grad_means2D, grad_colors_precomp, grad_semantics, grad_opacities, grad_means3D,
+                 grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            (grad_means2D, grad_colors_precomp, grad_semantics, grad_opacities, grad_means3D, grad_cov3Ds_precomp,
+             grad_sh, grad_scales, grad_rotations) = _C.rasterize_gaussians_backward(*args)
+
+        def _shaped(grad, like):
+            # absent optional inputs were `torch.Tensor([])`; autograd wants None (or a matching shape) for them
+            if like is None or like.numel() == 0:
+                return None
+            return grad.view(like.shape) if grad.numel() == like.numel() else grad
+
+        grads = (grad_means3D, grad_means2D, _shaped(grad_sh, sh), _shaped(grad_colors_precomp, colors_precomp),
+                 _shaped(grad_semantics, semantics), grad_opacities.view(ctx.opacity_shape), _shaped(grad_scales, scales),
+                 _shaped(grad_rotations, rotations), _shaped(grad_cov3Ds_precomp, cov3Ds_precomp), None)
+        return grads
+
+    @staticmethod
+    def trace(means3D, means2D, sh, colors_precomp, img_sem, opacities, scales, rotations, cov3Ds_precomp,
+              raster_settings):
+        args = (raster_settings.bg, means3D, colors_precomp, img_sem, opacities, scales, rotations,
+                raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
+                raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy,
+                raster_settings.image_height, raster_settings.image_width, sh, raster_settings.sh_degree,
+                raster_settings.campos, raster_settings.prefiltered, raster_settings.debug)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                (num_rendered, color, gau_sem, num_gsem, geomBuffer, binningBuffer,
+                 imgBuffer) = _C.rasterize_gaussians_trace(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            (num_rendered, color, gau_sem, num_gsem, geomBuffer, binningBuffer,
+             imgBuffer) = _C.rasterize_gaussians_trace(*args)
+        return color, gau_sem, num_gsem
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            raster_settings = self.raster_settings
+            visible = _C.mark_visible(positions, raster_settings.viewmatrix, raster_settings.projmatrix)
+        return visible
+
+    @staticmethod
+    def _check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, semantics=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+        self._check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if semantics is None:
+            semantics = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, semantics, opacities, scales, rotations,
+                                   cov3D_precomp, raster_settings)
+
+    def trace(self, means3D, means2D, opacities, shs=None, colors_precomp=None, img_sem=None, scales=None,
+              rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+        self._check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if img_sem is None:
+            img_sem = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return trace_gaussians(means3D, means2D, shs, colors_precomp, img_sem, opacities, scales, rotations,
+                               cov3D_precomp, raster_settings)

@@ -1,0 +1,238 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+Every test goes through the reference-shaped Python surface -> C ABI -> CUDA kernels and compares with
+(a) the CPU oracle on the same seeded inputs, (b) the reference's own CUDA core (oracle/_ref) when the
+prebuilt library travelled with the snapshot, (c) size-independent properties at BASELINE.json's full
+config-2 size.  Tolerances are the north star's: 1e-4 L-inf on images, 1e-3 of max on gradients.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from common import (assert_grads_close, assert_images_close, grad_report, image_report, run_cuda, run_oracle,
+                    run_reference_cuda, to_np)
+from goi_b200.scenes import SyntheticCamera, SyntheticGaussians, make_loss_weights, make_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_ok(S):
+    from oracle import refshim
+    return refshim.available(S)
+
+
+# ---------------------------------------------------------------------------------------------
+# (a) CUDA vs CPU oracle, config-1-sized cases (10k Gaussians, 256x256) + ragged / option variants
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,W,H,S,use_sh,use_cov,seed", [
+    (10_000, 256, 256, 0, True, False, 0),      # BASELINE config 1: RGB only
+    (10_000, 256, 256, 10, True, False, 0),     # the reference's shipped channel count
+    (10_000, 256, 256, 16, True, False, 1),
+    (6_000, 250, 197, 16, False, False, 2),     # ragged image, precomputed colours
+    (6_000, 200, 120, 4, True, True, 3),        # precomputed 3D covariance
+    (4_000, 160, 96, 32, True, False, 4),
+    (3_000, 128, 80, 64, True, False, 5),       # widest supported vector (reference cannot build S=64)
+    (3_000, 128, 80, 7, True, False, 6),        # S not a multiple of 4: scalar staging path
+    (3_000, 128, 80, 20, True, False, 7),       # S between kernel instantiations (padded lanes)
+])
+def test_cuda_matches_oracle(P, W, H, S, use_sh, use_cov, seed):
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    bg = torch.tensor([0.3, 0.5, 0.7])
+    w = make_loss_weights(S, W, H, seed)
+    ora = run_oracle(g, cam, bg, w, use_sh, use_cov)
+    cu = run_cuda(g, cam, bg, w, use_sh, use_cov)
+    assert np.array_equal(to_np(cu["radii"]), ora["radii"]), "radii differ"
+    # threshold flips (1-ulp expf / FMA differences between CPU and GPU) may touch isolated pixels
+    rep = assert_images_close(cu, ora, max_bad_frac=2e-4, what="cuda vs oracle")
+    keys = [k for k in common.GRAD_KEYS if k in cu["grads"]] + (["dL_dcolors"] if not use_sh else []) \
+        + (["dL_dcov3D"] if use_cov else [])
+    grep = assert_grads_close(cu["grads"], ora["grads"], rtol=2e-3, what="cuda vs oracle", keys=keys)
+    print("\n", rep, "\n", grep)
+
+
+# ---------------------------------------------------------------------------------------------
+# (b) CUDA vs the reference's own CUDA kernels (same compiler, same expression order)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,W,H,S,seed", [
+    (10_000, 256, 256, 0, 0),
+    (10_000, 256, 256, 10, 0),
+    (200_000, 800, 600, 16, 1),
+    (100_000, 640, 360, 32, 2),
+])
+def test_cuda_matches_reference_cuda(P, W, H, S, seed):
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    w = make_loss_weights(S, W, H, seed)
+    ref = run_reference_cuda(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert torch.equal(cu["radii"].cpu(), ref["radii"].cpu()), "radii differ from the reference kernels"
+    rep = assert_images_close(cu, ref, max_bad_frac=0.0, what="cuda vs reference cuda")
+    grep = assert_grads_close(cu["grads"], ref["grads"], what="cuda vs reference cuda")
+    print("\n", rep, "\n", grep)
+
+
+@pytest.mark.parametrize("P,W,H,S,seed", [(10_000, 256, 256, 10, 0), (8_000, 250, 197, 16, 3)])
+def test_oracle_pinned_by_reference_cuda(P, W, H, S, seed):
+    """The CPU oracle itself is checked against the real reference kernels (parity pin)."""
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    bg = torch.tensor([0.3, 0.5, 0.7])
+    w = make_loss_weights(S, W, H, seed)
+    ref = run_reference_cuda(g, cam, bg, w)
+    ora = run_oracle(g, cam, bg, w, wide=True)
+    assert np.array_equal(to_np(ref["radii"]), ora["radii"])
+    assert ref["num_rendered"] == ora["num_rendered"]
+    assert_images_close(ora, ref, max_bad_frac=2e-4, what="oracle vs reference cuda")
+    keys = list(common.GRAD_KEYS) + ["dL_dcolors", "dL_dconic", "dL_ddepths", "dL_dcov3D"]
+    assert_grads_close(ora["grads"], ref["grads"], rtol=2e-3, what="oracle vs reference cuda", keys=keys)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def _settings(cam, bg, device="cuda"):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    cam = cam.to(device)
+    return GaussianRasterizationSettings(cam.image_height, cam.image_width, math.tan(cam.FoVx / 2),
+                                         math.tan(cam.FoVy / 2), bg.to(device), 1.0, cam.world_view_transform,
+                                         cam.full_proj_transform, 3, cam.camera_center, False, False)
+
+
+def test_empty_scene():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    cam = SyntheticCamera(64, 48, math.radians(60))
+    rast = GaussianRasterizer(_settings(cam, torch.tensor([0.2, 0.4, 0.6])))
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    color, sem, radii, depth, alpha = rast(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), shs=z(0, 16, 3),
+                                           semantics=z(0, 16), scales=z(0, 3), rotations=z(0, 4))
+    assert color.shape == (3, 48, 64) and radii.shape == (0,)
+    assert float(color.abs().max()) == 0.0 and float(alpha.abs().max()) == 0.0   # reference: zero fill, no bg
+
+
+def test_all_culled_renders_background():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    g, cam, _ = make_scene(500, 64, 48, 16, 0)
+    g._xyz[:, 2] = -g._xyz[:, 2]                  # everything behind the camera
+    bg = torch.tensor([0.2, 0.4, 0.6])
+    cu = run_cuda(g, cam, bg, make_loss_weights(16, 64, 48, 0))
+    assert int((cu["radii"] > 0).sum()) == 0
+    assert torch.allclose(cu["color"], bg.cuda().view(3, 1, 1).expand(3, 48, 64))
+    assert float(cu["alpha"].abs().max()) == 0.0 and float(cu["semantics"].abs().max()) == 0.0
+    for k, v in cu["grads"].items():
+        assert v is None or float(v.abs().max()) == 0.0, k
+
+
+def test_huge_and_tiny_gaussians():
+    """One Gaussian covering every tile + sub-pixel Gaussians + zero-opacity ones."""
+    g, cam, bg = make_scene(300, 96, 64, 16, 9)
+    g._scaling[0] = torch.tensor([30.0, 30.0, 30.0]); g._xyz[0] = torch.tensor([0.0, 0.0, 5.0])
+    g._scaling[1:50] *= 1e-3
+    g._opacity[50:80] = 0.0
+    g._opacity[80:90] = 1.0
+    w = make_loss_weights(16, 96, 64, 9)
+    ora = run_oracle(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert np.array_equal(to_np(cu["radii"]), ora["radii"])
+    assert_images_close(cu, ora, max_bad_frac=5e-4, what="huge/tiny")
+    assert_grads_close(cu["grads"], ora["grads"], rtol=2e-3, what="huge/tiny")
+
+
+def test_equal_depth_ties_resolve_by_index():
+    """Stable sort contract: identical depths composite in ascending Gaussian index."""
+    P, W, H, S = 64, 48, 48, 4
+    g, cam, bg = make_scene(P, W, H, S, 11)
+    g._xyz[:, 2] = 4.0                              # all the same view-space depth
+    g._xyz[:, :2] *= 0.2
+    g._opacity[:] = 0.9
+    ora = run_oracle(g, cam, bg)
+    cu = run_cuda(g, cam, bg)
+    assert_images_close(cu, ora, max_bad_frac=0.0, what="depth ties")
+
+
+def test_mark_visible_and_trace():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from oracle import oracle
+    g, cam, bg = make_scene(2000, 96, 64, 10, 13)
+    g._xyz[::7, 2] *= -1
+    rast = GaussianRasterizer(_settings(cam, bg))
+    vis = rast.markVisible(g.get_xyz.cuda())
+    exp = oracle.mark_visible(g.get_xyz.numpy(), cam.world_view_transform.numpy(), cam.full_proj_transform.numpy())
+    assert np.array_equal(vis.cpu().numpy(), exp)
+
+    gen = torch.Generator().manual_seed(5)
+    img_sem = torch.rand(10, 64, 96, generator=gen)
+    gd = g.to("cuda")
+    color, gau_sem, num_gsem = rast.trace(means3D=gd.get_xyz, means2D=torch.zeros_like(gd.get_xyz),
+                                          opacities=gd.get_opacity, shs=gd.get_features, img_sem=img_sem.cuda(),
+                                          scales=gd.get_scaling, rotations=gd.get_rotation)
+    ca = common.cam_arrays(cam, bg)
+    exp = oracle.trace(means3D=g.get_xyz.numpy(), opacities=g.get_opacity.numpy(), shs=g.get_features.numpy(),
+                       scales=g.get_scaling.numpy(), rotations=g.get_rotation.numpy(), img_sem=img_sem.numpy(), **ca)
+    assert np.abs(color.cpu().numpy() - exp["color"]).max() <= 1e-4
+    # counts are integers: exact except for pairs whose alpha sits on the 0.005 / (1/255) thresholds
+    diff = np.abs(num_gsem.cpu().numpy() - exp["num_gsem"])
+    assert (diff > 0).mean() < 2e-3
+    rel = np.abs(gau_sem.cpu().numpy() - exp["gau_sem"]).max() / max(np.abs(exp["gau_sem"]).max(), 1e-9)
+    assert rel < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# (c) size-independent properties at the full BASELINE config-2 size (1M Gaussians, 1600x1000, S=16)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def big_scene():
+    g, cam, bg = make_scene(1_000_000, 1600, 1000, 16, 1)
+    return g.to("cuda"), cam.to("cuda"), bg.to("cuda")
+
+
+def test_full_size_determinism_and_bounds(big_scene):
+    g, cam, bg = big_scene
+    a = run_cuda(g, cam, bg)
+    b = run_cuda(g, cam, bg)
+    for k in ("color", "semantics", "depth", "alpha", "radii"):
+        assert torch.equal(a[k], b[k]), f"{k} not bit-reproducible"
+    assert float(a["alpha"].min()) >= 0.0 and float(a["alpha"].max()) <= 1.0 - 1e-4 + 1e-6
+    assert torch.isfinite(a["color"]).all() and torch.isfinite(a["semantics"]).all()
+
+
+def test_full_size_permutation_invariance(big_scene):
+    """Shuffling the Gaussian order must not change the image (random depths => no ties): exercises the
+    prefix sum, key emission, radix sort and tile ranges at full size."""
+    g, cam, bg = big_scene
+    a = run_cuda(g, cam, bg)
+    perm = torch.randperm(g.get_xyz.shape[0], device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    gp = SyntheticGaussians(*[t[perm].contiguous() for t in g.tensors()])
+    b = run_cuda(gp, cam, bg)
+    assert torch.equal(a["radii"][perm], b["radii"])
+    for k in ("color", "semantics", "depth", "alpha"):
+        assert float((a[k] - b[k]).abs().max()) <= 1e-5, k
+
+
+def test_full_size_payload_linearity_and_euler(big_scene):
+    """The composite is linear in the payload: out(s1 + s2) = out(s1) + out(s2); and for a linear loss
+    L = <w, out_sem>,  L = <sem, dL/dsem> (Euler), which ties backward to forward at full size."""
+    g, cam, bg = big_scene
+    S, H, W = 16, cam.image_height, cam.image_width
+    gen = torch.Generator("cuda").manual_seed(17)
+    s2 = torch.randn(g.get_semantics.shape, device="cuda", generator=gen)
+    o1 = run_cuda(g, cam, bg)
+    g2 = SyntheticGaussians(g.get_xyz, g.get_opacity, g.get_scaling, g.get_rotation, g.get_features, s2)
+    o2 = run_cuda(g2, cam, bg)
+    g12 = SyntheticGaussians(g.get_xyz, g.get_opacity, g.get_scaling, g.get_rotation, g.get_features,
+                             g.get_semantics + s2)
+    o12 = run_cuda(g12, cam, bg)
+    assert float((o12["semantics"] - o1["semantics"] - o2["semantics"]).abs().max()) <= 1e-4
+
+    w = make_loss_weights(S, W, H, 1, device="cuda")
+    wz = {k: torch.zeros_like(v) for k, v in w.items()}
+    wz["semantics"] = w["semantics"]
+    out = run_cuda(g, cam, bg, wz)
+    L = float((out["semantics"].double() * w["semantics"].double()).sum())
+    euler = float((g.get_semantics.double() * out["grads"]["dL_dsemantics"].double()).sum())
+    assert abs(L - euler) <= 1e-3 * max(abs(L), 1.0), (L, euler)
