@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec forward+backward of the GOI rasterizer hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+
+One "step" = one full training-view pass per GPU: render() forward (preprocess, binning, depth sort,
+composite of RGB + S semantic channels + depth + alpha) + backward of a fixed linear pseudo-loss
+L = sum(w * outputs) down to every per-Gaussian input (means, SH, semantics, opacity, scales,
+rotations).  Workload at N=1 = BASELINE.json configs[1] stand-in ("c2": 1M synthetic Gaussians,
+1600x1000, 16 semantic channels; the pretrained 'garden' scene is not on the box).
+N > 1: one process per GPU, each rank renders its own view per step against a full parameter replica
+(weak scaling) and the per-Gaussian gradients are summed with one NCCL all-reduce per step.
+
+JSON line (rank 0):
+  value     views/s with all inputs resident in HBM (CUDA events, max over ranks)
+  e2e       views/s through the same public API with the per-view inputs (camera + the pixel-space
+            supervision = loss-weight images) coming from pinned HOST memory every step and the loss
+            read back to the host; Gaussian parameters are model state and stay in HBM in both arms,
+            as in the reference's train.py
+  roofline  forward+backward composite kernels: algorithmic bytes B_comp / their CUDA-event
+            time inside the timed region, against the measured HBM peak
+  cpu_baseline  the CPU oracle port timed on the host cores on a bounded sample (reported only)
+`--impl reference` times the reference's OWN CUDA kernels + host glue (oracle/_ref, built from
+/root/reference by oracle/build.py) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "goi-hyperplane_b200"))
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (P, W, H, S, seed)   SURVEY.md section 8d
+    "c1": (10_000, 256, 256, 10, 0),
+    "c2": (1_000_000, 1600, 1000, 16, 1),
+    "c3": (1_000_000, 800, 600, 32, 2),
+    "c5_4": (1_000_000, 1280, 720, 4, 4), "c5_8": (1_000_000, 1280, 720, 8, 4),
+    "c5_16": (1_000_000, 1280, 720, 16, 4), "c5_32": (1_000_000, 1280, 720, 32, 4),
+    "c5_64": (1_000_000, 1280, 720, 64, 4),
+}
+N_VIEWS = 8      # distinct camera poses cycled through (small yaw/pitch jitter around the scene axis)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = int(self.samples[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples):
+                    out["reasons"].append(n)
+        except Exception:
+            pass
+        return out
+
+
+def make_views(W, H, device):
+    from goi_b200.scenes import SyntheticCamera
+    cams = []
+    for v in range(N_VIEWS):
+        yaw, pitch = math.radians(2.0 * math.sin(v * 0.9)), math.radians(1.5 * math.cos(v * 1.7))
+        cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+        Ry = torch.tensor([[cy, 0, sy, 0], [0, 1, 0, 0], [-sy, 0, cy, 0], [0, 0, 0, 1.0]])
+        Rx = torch.tensor([[1, 0, 0, 0], [0, cp, -sp, 0], [0, sp, cp, 0], [0, 0, 0, 1.0]])
+        cams.append(SyntheticCamera(W, H, math.radians(60.0), Rx @ Ry, device=device))
+    return cams
+
+
+def b_comp(R, W, H, S):
+    """algorithmic bytes of forward + backward composite for one view."""
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    return 16 * T + R * (128 + 12 * S) + W * H * (8 * S + 52)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from diff_gaussian_rasterization import _C
+    from gaussian_renderer import render
+    from goi_b200.scenes import PipeFlags, make_loss_weights, make_scene
+    from goi_b200 import view_parallel as vp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.lib()        # hard error if the CUDA library is missing: no fallback path
+
+    P, W, H, S, seed = CONFIGS[args.config]
+    g, _, bg = make_scene(P, W, H, S, seed)
+    g = g.to(dev).requires_grad_(True)
+    bg = bg.to(dev)
+    cams = make_views(W, H, dev)
+    pipe = PipeFlags()
+    w_dev = make_loss_weights(S, W, H, seed, device=dev)
+    params = [t for t in g.tensors() if t is not None]
+    flat = vp.FlatGradBuffer(params)           # .grad of every parameter is a view into one flat f32 buffer
+
+    def step(i, weights):
+        cam = cams[(i * world + rank) % N_VIEWS]
+        out = render(cam, g, pipe, bg)
+        loss = (out["render"] * weights["render"]).sum() + (out["semantics"] * weights["semantics"]).sum() \
+            + (out["depth"] * weights["depth"]).sum() + (out["alpha"] * weights["alpha"]).sum()
+        loss.backward()
+        if world > 1:
+            flat.all_reduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---------------- device-resident arm ----------------
+    for i in range(args.warmup):
+        flat.zero()
+        step(i, w_dev)
+    _C.timing_enable(True)
+    stage_acc, rs = {}, []
+    launches0 = _C.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    def resident_step(i):
+        flat.zero()
+        step(i, w_dev)
+        for k, v in _C.timing_read().items():       # syncs on this step's last kernel
+            stage_acc[k] = stage_acc.get(k, 0.0) + max(v, 0.0)
+        rs.append(_C.last_num_rendered)
+
+    ms_total = timed(resident_step, args.steps)
+    launches = _C.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    _C.timing_enable(False)
+    value = world * args.steps / (ms_total / 1e3)
+
+    # ---------------- end-to-end arm: per-view inputs from pinned host memory ----------------
+    host_w = [{k: v.cpu().pin_memory() for k, v in make_loss_weights(S, W, H, seed + j).items()} for j in range(2)]
+    h2d_bytes = sum(v.numel() * 4 for v in host_w[0].values()) + (16 + 16 + 3 + 3) * 4
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host_w[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for k in slots[s]:
+                slots[s][k].copy_(host_w[i % 2][k], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_step(i):
+        if i == 0:
+            prefetch(0)
+        if i + 1 < args.steps:
+            prefetch(i + 1)                          # overlaps this step's compute
+        s = i % 2
+        torch.cuda.current_stream().wait_event(ready[s])
+        flat.zero()
+        loss = step(i, slots[s])
+        freed[s].record()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)    # D2H read of the step's result
+
+    for ev in freed:
+        ev.record()
+    for i in range(min(2, args.warmup)):
+        e2e_step(i)
+    for ev in freed:
+        ev.record()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    R = sum(rs) / max(len(rs), 1)
+    t_comp = (stage_acc.get("composite_fwd", 0.0) + stage_acc.get("composite_bwd", 0.0)) / args.steps / 1e3
+    bytes_comp = b_comp(R, W, H, S)
+    achieved = bytes_comp / t_comp / 1e9 if t_comp > 0 else 0.0
+    line = {
+        "metric": "views/sec fwd+bwd @1M Gaussians,1600x1000,16ch; HBM GB/s vs roofline",
+        "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
+                               f"fwd+bwd of all four outputs, {N_VIEWS} camera poses",
+                   "views_per_step": world, "parallelism": f"view-dp{world}",
+                   "l2_policy": "inputs larger than L2 (300 MB parameters + 98 MB sort buffers per view)",
+                   "num_rendered_mean": round(R)},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_composite_fwd + k_composite_bwd",
+                     "algorithmic_bytes_per_view": int(bytes_comp), "kernel_ms_per_view": round(t_comp * 1e3, 4)},
+        "stages_ms_per_view": {k: round(v / args.steps, 4) for k, v in stage_acc.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    """The CPU oracle port on the host cores, on a bounded sample of the same workload: the same scene
+    generator at 1/4 of the pixels and Gaussians (same per-pixel density), scaled back by 4."""
+    from common_bench import oracle_fwd_bwd
+    P, W, H, S, seed = CONFIGS[args.config]
+    k = 4
+    t, cores = oracle_fwd_bwd(max(P // k, 1000), max(W // 2, 64), max(H // 2, 64), S, seed)
+    return {"value": round(1.0 / (t * k), 5), "unit": "views/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/goi_oracle.c fwd+bwd on P={P // k}, {W // 2}x{H // 2}, S={S} ({t:.2f} s; forward "
+                      f"tiles on {cores} OpenMP threads, reverse walk sequential), scaled x1/{k} to the full view"}
+
+
+def run_reference(args):
+    """The reference's own CUDA kernels + glue (oracle/_ref/libref_S*.so) on the same workload."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refshim
+    from goi_b200.scenes import make_loss_weights, make_scene
+    P, W, H, S, seed = CONFIGS[args.config]
+    if not refshim.available(S):
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libref_S{S}.so not built"}))
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g, _, bg = make_scene(P, W, H, S, seed)
+    g = g.to(dev)
+    bg = bg.to(dev)
+    cams = make_views(W, H, dev)
+    w = {k: v.contiguous() for k, v in make_loss_weights(S, W, H, seed, device=dev).items()}
+    rr = refshim.RefRasterizer(S)
+    tensors = dict(means3D=g.get_xyz.contiguous(), opacities=g.get_opacity.contiguous(),
+                   shs=g.get_features.contiguous(), semantics=g.get_semantics.contiguous(),
+                   scales=g.get_scaling.contiguous(), rotations=g.get_rotation.contiguous())
+
+    def step(i):
+        cam = cams[i % N_VIEWS]
+        rr.forward(W=W, H=H, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+                   campos=cam.camera_center, tanfovx=math.tan(cam.FoVx / 2), tanfovy=math.tan(cam.FoVy / 2), bg=bg,
+                   **tensors)
+        rr.backward(w["render"], w["semantics"], w["depth"], w["alpha"])
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    value = args.steps / (ms / 1e3)
+    line = {
+        "impl": "reference",
+        "metric": "views/sec fwd+bwd @1M Gaussians,1600x1000,16ch; HBM GB/s vs roofline",
+        "value": round(value, 3), "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
+                               f"fwd+bwd of all four outputs, {N_VIEWS} camera poses",
+                   "num_rendered": rr.num_rendered, "requested_gpus": world},
+        "clocks": clocks,
+        "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": 1, "kind": "reference",
+                         "sample": "the reference's own CUDA rasterizer (cuda_rasterizer/*.cu compiled unmodified "
+                                   "for sm_100a) driven by a single host thread incl. its blocking num_rendered "
+                                   "read-back and zero fills; the reference has no CPU rasterizer"},
+        "e2e": {"value": round(value, 3), "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

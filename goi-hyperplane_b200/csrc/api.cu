@@ -8,6 +8,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 
 namespace goi {
 
@@ -35,6 +37,39 @@ static int debug_sync(const goi_view* v, cudaStream_t st, const char* where)
         if (e != cudaSuccess) return cuda_fail(e, where);
     }
     return GOI_OK;
+}
+
+// ---- measurement hooks --------------------------------------------------------------------------
+struct Timing {
+    bool enabled = false, created = false;
+    cudaEvent_t ev[ST_COUNT][2];
+    bool valid[ST_COUNT] = {};
+};
+// Process-wide (not thread-local): PyTorch runs autograd's backward on its own worker thread, and the
+// forward and backward of one view must land in the same record.  Measurement only; guarded by a mutex.
+static Timing g_timing;
+static std::mutex g_timing_mu;
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void stage_begin(Stage s, cudaStream_t st)
+{
+    Timing& t = g_timing;
+    if (!t.enabled) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (!t.created) {
+        for (int i = 0; i < ST_COUNT; ++i) { cudaEventCreate(&t.ev[i][0]); cudaEventCreate(&t.ev[i][1]); }
+        t.created = true;
+    }
+    cudaEventRecord(t.ev[s][0], st);
+}
+void stage_end(Stage s, cudaStream_t st)
+{
+    Timing& t = g_timing;
+    if (!t.enabled || !t.created) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    cudaEventRecord(t.ev[s][1], st);
+    t.valid[s] = true;
 }
 
 template <typename T>
@@ -132,6 +167,36 @@ using namespace goi;
 extern "C" {
 
 int goi_abi_version(void) { return GOI_ABI_VERSION; }
+
+int goi_timing_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing.enabled = on != 0;
+    for (int i = 0; i < ST_COUNT; ++i) g_timing.valid[i] = false;
+    return GOI_OK;
+}
+int goi_timing_read(float* ms)
+{
+    if (!ms) return fail(GOI_ERR_INVALID_ARG, "null ms");
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (int i = 0; i < ST_COUNT; ++i) {
+        ms[i] = -1.f;
+        if (g_timing.created && g_timing.valid[i]) {
+            cudaError_t e = cudaEventSynchronize(g_timing.ev[i][1]);
+            if (e != cudaSuccess) return cuda_fail(e, "timing sync");
+            e = cudaEventElapsedTime(&ms[i], g_timing.ev[i][0], g_timing.ev[i][1]);
+            if (e != cudaSuccess) return cuda_fail(e, "timing read");
+        }
+    }
+    return GOI_OK;
+}
+const char* goi_stage_name(int stage)
+{
+    static const char* names[ST_COUNT] = {"preprocess", "prefix_sum", "key_emit", "radix_sort", "tile_ranges",
+                                          "composite_fwd", "zero_grads", "composite_bwd", "preprocess_bwd"};
+    return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
+}
+uint64_t goi_launch_count(void) { return g_launches.load(); }
 const char* goi_last_error(void) { return g_err; }
 
 size_t goi_geom_bytes(int32_t P, int32_t S) { return carve_geom(nullptr, P, S).total_bytes; }
@@ -151,9 +216,9 @@ int goi_forward_prepare(const goi_view* view, const goi_gaussians* g, int32_t* r
     cudaStream_t st = (cudaStream_t)stream;
     GeomState gs = carve_geom((char*)geom_buf, g->P, g->S);
 
-    GOI_CUDA(launch_preprocess_fwd(*view, *g, radii, gs, st), "preprocess");
+    { StageScope sc(ST_PREPROCESS, st); GOI_CUDA(launch_preprocess_fwd(*view, *g, radii, gs, st), "preprocess"); }
     if ((rc = debug_sync(view, st, "preprocess")) != GOI_OK) return rc;
-    GOI_CUDA(run_scan(gs, g->P, st), "prefix sum");
+    { StageScope sc(ST_SCAN, st); GOI_CUDA(run_scan(gs, g->P, st), "prefix sum"); }
     // the one host sync of the path (reference: cudaMemcpy at rasterizer_impl.cu:285)
     Meta host_meta;
     GOI_CUDA(cudaMemcpyAsync(&host_meta, gs.meta, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "read num_rendered");
@@ -194,7 +259,7 @@ int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_f
     int selector = 0;
     GOI_CUDA(run_binning(*view, g->P, out->radii, gs, bs, is, num_rendered, &selector, st), "binning");
     if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
-    GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], is, st), "composite forward");
+    { StageScope sc(ST_COMPOSITE_FWD, st); GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], is, st), "composite forward"); }
     return debug_sync(view, st, "composite forward");
 }
 
@@ -242,18 +307,21 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
     BinningState bs = carve_binning((char*)binning_buf, num_rendered);
 
     // accumulators of the composite backward (everything else is fully written by k_preprocess_bwd)
+    stage_begin(ST_ZERO, st);
     GOI_CUDA(cudaMemsetAsync(out->dL_dmean2D, 0, sizeof(float) * 3 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_dconic, 0, sizeof(float) * 4 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_ddepth, 0, sizeof(float) * P, st), "zero grads");
     if (g->S > 0) GOI_CUDA(cudaMemsetAsync(out->dL_dsemantic, 0, sizeof(float) * (size_t)g->S * P, st), "zero grads");
+    stage_end(ST_ZERO, st);
 
     if (num_rendered > 0) {
+        StageScope sc(ST_COMPOSITE_BWD, st);
         GOI_CUDA(launch_composite_bwd(*view, *g, *in, *out, gs, bs.vals[0], is, st), "composite backward");
-        if ((rc = debug_sync(view, st, "composite backward")) != GOI_OK) return rc;
     }
-    GOI_CUDA(launch_preprocess_bwd(*view, *g, *in, *out, gs, st), "preprocess backward");
+    if ((rc = debug_sync(view, st, "composite backward")) != GOI_OK) return rc;
+    { StageScope sc(ST_PREPROCESS_BWD, st); GOI_CUDA(launch_preprocess_bwd(*view, *g, *in, *out, gs, st), "preprocess backward"); }
     return debug_sync(view, st, "preprocess backward");
 }
 

@@ -13,6 +13,7 @@
 // All of this is pure HBM streaming: 12 B written per instance by the emitter, a 64-bit-key /
 // 32-bit-value onesweep radix sort, 8 B read per instance for the range scan.
 #include "goi_internal.cuh"
+#include "goi_cull.cuh"
 #include <cub/cub.cuh>
 
 namespace goi {
@@ -38,6 +39,7 @@ cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st)
     if (need > gs.scan_temp_bytes) return cudaErrorMemoryAllocation;
     size_t bytes = gs.scan_temp_bytes;
     e = cub::DeviceScan::InclusiveSum(gs.scan_temp, bytes, gs.tiles_touched, gs.point_offsets, P, st);
+    count_launches(2);                         // CUB: init + scan kernels
     if (e != cudaSuccess) return e;
     // R = point_offsets[P-1], kept on the device too (Meta::num_rendered)
     return cudaMemcpyAsync(&gs.meta->num_rendered, gs.point_offsets + (P - 1), sizeof(uint32_t),
@@ -45,20 +47,27 @@ cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st)
 }
 
 // One thread per Gaussian; emits its rect's tiles row-major, exactly the reference's loop nest.
-__global__ void __launch_bounds__(256) k_emit_keys(int P, const float4* __restrict__ rgbd,
+__global__ void __launch_bounds__(256) k_emit_keys(int P, const float4* __restrict__ geo,
+                                                   const float4* __restrict__ rgbd,
                                                    const uint32_t* __restrict__ offsets,
                                                    const uint2* __restrict__ rect, const int32_t* __restrict__ radii,
-                                                   int gx, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+                                                   int gx, int W, int H, uint64_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     if (!(radii[idx] > 0)) return;
     uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
+    const uint32_t end = offsets[idx];
+    if (off == end) return;
     const uint2 rc = rect[idx];
     const uint32_t minx = rc.x & 0xffffu, miny = rc.x >> 16, maxx = rc.y & 0xffffu, maxy = rc.y >> 16;
     const uint32_t depth_bits = __float_as_uint(rgbd[idx].w);
+    const float4 g0 = geo[2 * idx], g1 = geo[2 * idx + 1];
     for (uint32_t y = miny; y < maxy; ++y)
         for (uint32_t x = minx; x < maxx; ++x) {
+            if (!tile_may_contribute(g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, (int)x, (int)y, W, H)) continue;
+            if (off >= end) return;           // cannot happen (same bit-exact test as the count); never overrun
             uint64_t key = (uint64_t)(y * (uint32_t)gx + x);
             key <<= 32;
             key |= depth_bits;
@@ -110,7 +119,11 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     *selector_out = 0;
     if (R <= 0) return cudaSuccess;
 
-    k_emit_keys<<<(P + 255) / 256, 256, 0, st>>>(P, gs.rgbd, gs.point_offsets, gs.rect, radii, gx, bs.keys[0], bs.vals[0]);
+    stage_begin(ST_EMIT, st);
+    k_emit_keys<<<(P + 255) / 256, 256, 0, st>>>(P, gs.geo, gs.rgbd, gs.point_offsets, gs.rect, radii, gx, v.width, v.height,
+                                                 bs.keys[0], bs.vals[0]);
+    stage_end(ST_EMIT, st);
+    count_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
@@ -122,11 +135,17 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     if (e != cudaSuccess) return e;
     if (need > bs.sort_temp_bytes) return cudaErrorMemoryAllocation;
     size_t bytes = bs.sort_temp_bytes;
+    stage_begin(ST_SORT, st);
     e = cub::DeviceRadixSort::SortPairs(bs.sort_temp, bytes, dk, dv, R, 0, end_bit, st);
+    stage_end(ST_SORT, st);
+    count_launches(2 + (end_bit + 7) / 8);     // onesweep: histogram + scan + one kernel per 8-bit digit
     if (e != cudaSuccess) return e;
     *selector_out = 0;
 
+    stage_begin(ST_RANGES, st);
     k_tile_ranges<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, dk.Current(), is.ranges);
+    stage_end(ST_RANGES, st);
+    count_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // The sorted Gaussian list always ends up in vals[0] so that the backward (which only has the

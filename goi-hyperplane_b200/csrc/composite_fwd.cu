@@ -11,19 +11,21 @@
 // three step functions take the same branch.
 //
 // B200 design (what differs from the reference kernel):
-//   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block (compact footprint =>
-//     more whole-warp rejects than the reference's 16x2 rows);
+//   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block;
 //   * instances are staged 128 at a time into shared memory with cp.async (LDGSTS), double
 //     buffered, INCLUDING the payload row (rgb, depth, S semantic floats, float4-vectorised):
 //     the reference re-reads S+4 scalars from global memory per contributing pair (:360-364);
-//   * per Gaussian record is two float4 (xy+conic, conic.z+opacity+power_cut) -> two broadcast
-//     LDS.128 per pair instead of three scattered arrays;
-//   * power_cut (precomputed -ln(255 o) - margin) rejects provably non-contributing pairs
-//     before the expf; a warp vote skips the payload FMAs when no lane blends;
+//   * per-warp culling: the 32 lanes test 32 staged instances in parallel against the warp's 8x4
+//     pixel rectangle with the exact concave-quadratic bound of goi_cull.cuh, ballot, and the warp
+//     then walks only the set bits (in list order).  A rejected (warp, instance) costs ~1.5
+//     instructions instead of a full per-pixel evaluation;
+//   * power_cut (precomputed -ln(255 o) - margin) rejects provably non-contributing pixels
+//     before the expf;
 //   * S is a run-time value: kernels are instantiated per float4-group count (0..16 groups).
 // HBM roofline: algorithmic bytes per instance = 4 (id) + 32 (geo) + 16 (rgbd) + 4S (sem);
 // per pixel = 4(S+5) + 4 written.
 #include "goi_internal.cuh"
+#include "goi_cull.cuh"
 
 namespace goi {
 
@@ -40,19 +42,24 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 {
     constexpr int ROW = 1 + NS4;                       // float4 per payload row: (r,g,b,depth) + semantics
     extern __shared__ float4 smem[];
-    float4* s_geo = smem;                              // [2][BATCH][2]
-    float4* s_pay = smem + 2 * BATCH * 2;              // [2][BATCH][ROW]
+    float4* s_g0 = smem;                               // [2][BATCH] (mean.x, mean.y, conic.x, conic.y)
+    float4* s_g1 = smem + 2 * BATCH;                   // [2][BATCH] (conic.z, opacity, power_cut, -)
+    float4* s_pay = smem + 4 * BATCH;                  // [2][BATCH][ROW]
     __shared__ int s_id[2][BATCH];                     // Gaussian ids (trace mode scatters by id)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
-    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int wx0 = tx * TILE + (warp & 1) * 8, wy0 = ty * TILE + (warp >> 1) * 4;   // warp's 8x4 block
+    const int px = wx0 + (lane & 7);
+    const int py = wy0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
+    // pixel-centre rectangle of this warp, clipped to the image
+    const float rx0 = (float)wx0, rx1 = (float)min(wx0 + 7, W - 1);
+    const float ry0 = (float)wy0, ry1 = (float)min(wy0 + 3, H - 1);
 
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -72,8 +79,8 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
             const int j = wi / PARTS, part = wi % PARTS;
             const uint32_t id = point_list[base + j];
             if (part == 0) {
-                cp_async16(&s_geo[(buf * BATCH + j) * 2], &geo[2 * (size_t)id]);
-                cp_async16(&s_geo[(buf * BATCH + j) * 2 + 1], &geo[2 * (size_t)id + 1]);
+                cp_async16(&s_g0[buf * BATCH + j], &geo[2 * (size_t)id]);
+                cp_async16(&s_g1[buf * BATCH + j], &geo[2 * (size_t)id + 1]);
                 cp_async16(&s_pay[(buf * BATCH + j) * ROW], &rgbd[id]);
                 if (TRACE) s_id[buf][j] = (int)id;
             } else {
@@ -95,58 +102,71 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     float Cs[NS4 > 0 ? 4 * NS4 : 1];
 #pragma unroll
     for (int i = 0; i < (NS4 > 0 ? 4 * NS4 : 1); ++i) Cs[i] = 0.f;
-    bool done = !inside;
+    int done = inside ? 0 : 1;                          // int, not bool: keeps the loop free of byte packing
+    bool warp_done = __all_sync(0xffffffffu, done);
+    const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
 
     if (nb > 0) stage(0);
     for (int b = 0; b < nb; ++b) {
         cp_async_wait_all();
         if (__syncthreads_count(!done) == 0) break;     // batch b landed; batch b-1 fully consumed
         if (b + 1 < nb) stage(b + 1);
+        if (warp_done) continue;
 
         const int buf = b & 1;
         const int cnt = min(BATCH, n - b * BATCH);
-        const float4* sg = s_geo + buf * BATCH * 2;
-        const float4* sp = s_pay + buf * BATCH * ROW;
-        if (__all_sync(0xffffffffu, done)) continue;
-        for (int j = 0; j < cnt; ++j) {
-            const float4 g0 = sg[2 * j];
-            const float4 g1 = sg[2 * j + 1];
-            const float dx = g0.x - pxf, dy = g0.y - pyf;
-            const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-            bool hit = !done && !(power > 0.0f) && !(power < g1.z);
-            if (!__any_sync(0xffffffffu, hit)) continue;
-            float alpha = 0.f, test_T = 0.f;
-            if (hit) {
-                alpha = fminf(0.99f, g1.y * expf(power));
-                if (alpha < 1.0f / 255.0f) hit = false;
-                else {
-                    test_T = T * (1 - alpha);
-                    if (test_T < 0.0001f) { done = true; hit = false; }
-                }
+        const uint32_t ag0 = a_g0 + buf * BATCH * 16, ag1 = a_g1 + buf * BATCH * 16;
+        const uint32_t apay = a_pay + buf * BATCH * ROW * 16;
+        const uint32_t list_base = (uint32_t)(b * BATCH + 1);
+        for (int c0 = 0; c0 < cnt && !warp_done; c0 += 32) {
+            // lanes test 32 instances in parallel against this warp's pixel rectangle
+            bool keep = false;
+            if (c0 + lane < cnt) {
+                const float4 a = lds128(ag0 + (c0 + lane) * 16);
+                const float4 q = lds128(ag1 + (c0 + lane) * 16);
+                keep = rect_may_contribute(a.x, a.y, a.z, a.w, q.x, q.z, rx0, rx1, ry0, ry1);
             }
-            if (__any_sync(0xffffffffu, hit)) {
-                const float w = hit ? alpha * T : 0.f;
-                const float4 p0 = sp[j * ROW];
-                C0 = fmaf(p0.x, w, C0); C1 = fmaf(p0.y, w, C1); C2 = fmaf(p0.z, w, C2);
-                if (!TRACE) {
-                    Dacc = fmaf(p0.w, w, Dacc);
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            while (m) {
+                const int j = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 g0 = lds128(ag0 + j * 16);
+                const float4 g1 = lds128(ag1 + j * 16);
+                const float dx = g0.x - pxf, dy = g0.y - pyf;
+                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                // branch-free evaluation (values of rejected lanes are computed and discarded)
+                const float alpha = fminf(0.99f, g1.y * expf(power));
+                const float test_T = T * (1 - alpha);
+                const bool valid = !done && !(power > 0.0f) && !(power < g1.z) && !(alpha < 1.0f / 255.0f);
+                const bool fin = valid && (test_T < 0.0001f);           // pixel saturates: not blended
+                const bool hit = valid && !fin;
+                done |= fin ? 1 : 0;
+                if (__any_sync(0xffffffffu, hit)) {
+                    const float w = hit ? alpha * T : 0.f;
+                    const uint32_t ap = apay + j * (ROW * 16);
+                    const float4 p0 = lds128(ap);
+                    C0 = fmaf(p0.x, w, C0); C1 = fmaf(p0.y, w, C1); C2 = fmaf(p0.z, w, C2);
+                    if (!TRACE) {
+                        Dacc = fmaf(p0.w, w, Dacc);
 #pragma unroll
-                    for (int k = 0; k < NS4; ++k) {
-                        const float4 s4 = sp[j * ROW + 1 + k];
-                        Cs[4 * k + 0] = fmaf(s4.x, w, Cs[4 * k + 0]);
-                        Cs[4 * k + 1] = fmaf(s4.y, w, Cs[4 * k + 1]);
-                        Cs[4 * k + 2] = fmaf(s4.z, w, Cs[4 * k + 2]);
-                        Cs[4 * k + 3] = fmaf(s4.w, w, Cs[4 * k + 3]);
+                        for (int k = 0; k < NS4; ++k) {
+                            const float4 s4 = lds128(ap + 16 + 16 * k);
+                            Cs[4 * k + 0] = fmaf(s4.x, w, Cs[4 * k + 0]);
+                            Cs[4 * k + 1] = fmaf(s4.y, w, Cs[4 * k + 1]);
+                            Cs[4 * k + 2] = fmaf(s4.z, w, Cs[4 * k + 2]);
+                            Cs[4 * k + 3] = fmaf(s4.w, w, Cs[4 * k + 3]);
+                        }
+                    } else if (hit && alpha > 0.005) {
+                        // traceCUDA, forward.cu:521-526, with atomics instead of the reference's racy `+=`
+                        const int id = s_id[buf][j];
+                        for (int ch = 0; ch < S; ++ch) atomicAdd(&gau_sem[(size_t)id * S + ch], img_sem[ch * HW + pix]);
+                        atomicAdd(&num_gsem[id], count_per_channel ? S : 1);
                     }
-                } else if (hit && alpha > 0.005) {
-                    // traceCUDA, forward.cu:521-526, with atomics instead of the reference's racy `+=`
-                    const int id = s_id[buf][j];
-                    for (int ch = 0; ch < S; ++ch) atomicAdd(&gau_sem[(size_t)id * S + ch], img_sem[ch * HW + pix]);
-                    atomicAdd(&num_gsem[id], count_per_channel ? S : 1);
+                    T = hit ? test_T : T;
+                    last_contributor = hit ? list_base + (uint32_t)j : last_contributor;
                 }
-                if (hit) { T = test_T; last_contributor = (uint32_t)(b * BATCH + j + 1); }
+                if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
-            if (__all_sync(0xffffffffu, done)) break;
         }
     }
 
@@ -183,6 +203,7 @@ static cudaError_t launch_fwd_t(const goi_view& v, const goi_gaussians& g, const
                                                    g.semantics, g.S, sem_vec, v.background, out_color, out_sem,
                                                    out_depth, out_alpha, is.n_contrib, img_sem, gau_sem, num_gsem,
                                                    count_per_channel);
+    count_launches(1);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,66 @@
+// goi_cull.cuh -- exact "can this Gaussian reach alpha >= 1/255 anywhere in this pixel rectangle?" test.
+//
+// The reference blends a (pixel, Gaussian) pair only if power <= 0 and opacity*exp(power) >= 1/255
+// (cuda_rasterizer/forward.cu:341-351), where power(d) = -0.5(A dx^2 + C dy^2) - B dx dy is a concave
+// quadratic of d = mean - pixel with its maximum 0 at the mean.  Over a rectangle that does not contain
+// the mean, a concave function attains its maximum on the boundary, and on each edge it is a 1-D concave
+// parabola with a closed-form (clamped) maximiser.  rect_max_power() returns that exact maximum, so
+//     rect_max_power(...) < power_cut - kCullSlack
+// PROVES that no pixel of the rectangle can blend this Gaussian (power_cut = -ln(255 o) - 0.01 is stored
+// per Gaussian by preprocess; the slack covers float rounding of this evaluation, which is < 1e-3 in the
+// exponent because the +0.3 low-pass bounds the conic entries by 1/0.3).  Used twice: per 16x16 tile at
+// key emission (fewer instances to sort and walk) and per 8x4 warp block inside the composites.  Only
+// provably non-contributing pairs are removed; rendered values are unchanged.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace goi {
+
+constexpr float kCullSlack = 0.01f;
+
+// Explicitly rounded (no compiler-chosen FMA contraction): preprocess counts tiles and k_emit_keys emits
+// them with this same function, and the two MUST agree bit for bit.
+__device__ __forceinline__ float pair_power(float A, float B, float C, float dx, float dy)
+{
+    const float q = __fmaf_rn(__fmul_rn(C, dy), dy, __fmul_rn(__fmul_rn(A, dx), dx));
+    return __fmaf_rn(-0.5f, q, -__fmul_rn(__fmul_rn(B, dx), dy));
+}
+
+// Pixel rectangle [x0,x1] x [y0,y1] (pixel-centre coordinates, inclusive).
+__device__ __forceinline__ float rect_max_power(float mx, float my, float A, float B, float C,
+                                                float x0, float x1, float y0, float y1)
+{
+    const float dx0 = __fsub_rn(mx, x1), dx1 = __fsub_rn(mx, x0);      // d = mean - pixel
+    const float dy0 = __fsub_rn(my, y1), dy1 = __fsub_rn(my, y0);
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return 0.f;   // mean inside the rectangle
+    const float nb_c = __fmul_rn(-B, __frcp_rn(C));   // argmax_dy power(dx, .) = -B dx / C
+    const float nb_a = __fmul_rn(-B, __frcp_rn(A));   // argmax_dx power(., dy) = -B dy / A
+    // (a misplaced maximiser only changes the value to second order; clamping is exact)
+    float dy = fminf(fmaxf(__fmul_rn(nb_c, dx0), dy0), dy1);
+    float best = pair_power(A, B, C, dx0, dy);
+    dy = fminf(fmaxf(__fmul_rn(nb_c, dx1), dy0), dy1);
+    best = fmaxf(best, pair_power(A, B, C, dx1, dy));
+    float dx = fminf(fmaxf(__fmul_rn(nb_a, dy0), dx0), dx1);
+    best = fmaxf(best, pair_power(A, B, C, dx, dy0));
+    dx = fminf(fmaxf(__fmul_rn(nb_a, dy1), dx0), dx1);
+    best = fmaxf(best, pair_power(A, B, C, dx, dy1));
+    return best;
+}
+
+// true = keep (not provably empty).  NaNs compare false => keep.
+__device__ __forceinline__ bool rect_may_contribute(float mx, float my, float A, float B, float C, float power_cut,
+                                                    float x0, float x1, float y0, float y1)
+{
+    return !(rect_max_power(mx, my, A, B, C, x0, x1, y0, y1) < __fsub_rn(power_cut, kCullSlack));
+}
+
+// Tile (tx,ty) of a W x H image.
+__device__ __forceinline__ bool tile_may_contribute(float mx, float my, float A, float B, float C, float power_cut,
+                                                    int tx, int ty, int W, int H)
+{
+    const float x0 = (float)(tx * 16), y0 = (float)(ty * 16);
+    const float x1 = (float)min(tx * 16 + 15, W - 1), y1 = (float)min(ty * 16 + 15, H - 1);
+    return rect_may_contribute(mx, my, A, B, C, power_cut, x0, x1, y0, y1);
+}
+
+}  // namespace goi

@@ -67,6 +67,18 @@ inline int sem_groups(int S) {           // float4 groups the composite kernels 
     return 16;
 }
 
+// ---- measurement hooks (thread-local; see goi_timing_enable in goi_raster.h) -------------------
+enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES, ST_COMPOSITE_FWD, ST_ZERO, ST_COMPOSITE_BWD,
+             ST_PREPROCESS_BWD, ST_COUNT };
+void stage_begin(Stage s, cudaStream_t st);
+void stage_end(Stage s, cudaStream_t st);
+void count_launches(int n);
+struct StageScope {
+    Stage s; cudaStream_t st;
+    StageScope(Stage s_, cudaStream_t st_) : s(s_), st(st_) { stage_begin(s, st); }
+    ~StageScope() { stage_end(s, st); }
+};
+
 // ---- launchers (each returns cudaGetLastError() of its launches) -----------------------------
 cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int32_t* radii,
                                   const GeomState& gs, cudaStream_t st);
@@ -101,6 +113,19 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+// Explicit 32-bit shared-window addressing: keeps the hot loops free of generic->shared conversions.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t s, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }

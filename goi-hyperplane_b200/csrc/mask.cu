@@ -135,6 +135,7 @@ static cudaError_t launch_mask_t(const goi_mask_args& a, cudaStream_t st)
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, 256, smem, st>>>(a.N, a.S, a.K, a.stride_n, a.stride_c, a.x, a.mlp_weight, a.mlp_bias,
                                               a.sim_table, a.thresh, a.sim, a.bg_mask, a.idx);
+    count_launches(1);
     return cudaGetLastError();
 }
 

@@ -18,6 +18,7 @@
 //   geo[2i+1] = (conic.z, opacity, power_cut, 0)              instance costs 2 x 16 B cp.async
 //   rgbd[i]   = (r, g, b, depth)
 #include "goi_internal.cuh"
+#include "goi_cull.cuh"
 
 namespace goi {
 
@@ -221,7 +222,13 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     geo[2 * idx + 1] = make_float4(conic.z, opacity, power_cut, 0.f);
     rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, p_view.z);
     rect[idx] = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
-    tiles_touched[idx] = (uint32_t)((maxy - miny) * (maxx - minx));
+    // Instances = tiles of the reference rectangle that can actually reach alpha >= 1/255 (goi_cull.cuh).
+    // k_emit_keys repeats exactly this test, so the prefix sum and the emission agree.
+    uint32_t touched = 0;
+    for (int ty = miny; ty < maxy; ++ty)
+        for (int tx = minx; tx < maxx; ++tx)
+            touched += tile_may_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, power_cut, tx, ty, W, H) ? 1u : 0u;
+    tiles_touched[idx] = touched;
 }
 
 cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int32_t* radii, const GeomState& gs,
@@ -237,6 +244,7 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
         g.cov3D_precomp, g.colors_precomp, v.viewmatrix, v.projmatrix, v.cam_pos, v.width, v.height,
         v.tan_fovx, v.tan_fovy, focal_x, focal_y, gx, gy, v.prefiltered, radii, gs.geo, gs.rgbd, gs.cov3D,
         gs.clamped, gs.tiles_touched, gs.rect, gs.meta);
+    count_launches(1);
     return cudaGetLastError();
 }
 
@@ -492,6 +500,7 @@ cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, con
         out.dL_dmean2D, out.dL_dconic, out.dL_dcolor, out.dL_ddepth,
         out.dL_dmean3D, out.dL_dcov3D, g.shs ? out.dL_dsh : nullptr,
         g.scales ? out.dL_dscale : nullptr, g.scales ? out.dL_drot : nullptr);
+    count_launches(1);
     return cudaGetLastError();
 }
 

@@ -100,7 +100,13 @@ SYMBOLS = {
     "goi_mask": (C.c_int, [C.POINTER(goi_mask_args), C.c_void_p]),
     "goi_read_stats": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.POINTER(goi_stats)]),
+    "goi_timing_enable": (C.c_int, [C.c_int]),
+    "goi_timing_read": (C.c_int, [C.POINTER(C.c_float)]),
+    "goi_stage_name": (C.c_char_p, [C.c_int]),
+    "goi_launch_count": (C.c_uint64, []),
 }
+GOI_NUM_STAGES = 9
+last_num_rendered = 0      # R of the most recent forward on this thread (bench.py's roofline arithmetic)
 
 _lib = None
 
@@ -214,6 +220,8 @@ def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotatio
         _check(L.goi_forward_render(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
                                     binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, R.value, stream),
                "goi_forward_render")
+    global last_num_rendered
+    last_num_rendered = int(R.value)
     return int(R.value), out_color, out_sem, out_depth, out_alpha, radii, geom, binning, img
 
 
@@ -349,6 +357,21 @@ def hyperplane_mask(x, mlp_weight, mlp_bias, lut, hyperplane_w, hyperplane_b=0.0
                           bg.data_ptr() if N else None, idx.data_ptr() if (want_idx and N) else None)
         _check(L.goi_mask(C.byref(a), _stream(dev)), "goi_mask")
     return sim, bg, idx
+
+
+def timing_enable(on: bool) -> None:
+    _check(lib().goi_timing_enable(int(on)), "goi_timing_enable")
+
+
+def timing_read() -> dict:
+    """ms of the most recent occurrence of every pipeline stage (synchronises on their events)."""
+    buf = (C.c_float * GOI_NUM_STAGES)()
+    _check(lib().goi_timing_read(buf), "goi_timing_read")
+    return {lib().goi_stage_name(i).decode(): float(buf[i]) for i in range(GOI_NUM_STAGES)}
+
+
+def launch_count() -> int:
+    return int(lib().goi_launch_count())
 
 
 def read_stats(raster_settings_view, gaussians_struct, geom, radii, device):

@@ -48,9 +48,11 @@ class SyntheticCamera:
         self.camera_center = self.world_view_transform.inverse()[3, :3].contiguous()
 
     def to(self, device):
+        import copy
+        c = copy.copy(self)
         for k in ("world_view_transform", "projection_matrix", "full_proj_transform", "camera_center"):
-            setattr(self, k, getattr(self, k).to(device))
-        return self
+            setattr(c, k, getattr(self, k).to(device))
+        return c
 
 
 def look_at_world_to_view(eye, target=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0)) -> torch.Tensor:

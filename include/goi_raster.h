@@ -252,6 +252,19 @@ int goi_read_stats(const goi_view* view, const goi_gaussians* g,
                    const void* geom_buf, const int32_t* radii,
                    void* stream, goi_stats* stats);
 
+/* ---- per-stage device timing + launch accounting (measurement hooks for bench.py).
+ * When enabled (process-wide), every pipeline stage is bracketed by CUDA events on the
+ * caller's stream; goi_timing_read synchronises on them and returns the duration in ms of the
+ * most recent occurrence of each stage (-1 if it did not run).  Stage order:
+ *   0 preprocess  1 prefix-sum  2 key-emit  3 radix-sort  4 tile-ranges  5 composite-forward
+ *   6 zero-grads  7 composite-backward  8 preprocess-backward
+ * goi_launch_count returns how many kernels (own kernels + CUB's) the library has launched. */
+#define GOI_NUM_STAGES 9
+int         goi_timing_enable(int on);
+int         goi_timing_read(float* ms /* [GOI_NUM_STAGES] */);
+const char* goi_stage_name(int stage);
+uint64_t    goi_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

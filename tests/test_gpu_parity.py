@@ -123,7 +123,7 @@ def test_all_culled_renders_background():
     cu = run_cuda(g, cam, bg, make_loss_weights(16, 64, 48, 0))
     assert int((cu["radii"] > 0).sum()) == 0
     assert torch.allclose(cu["color"], bg.cuda().view(3, 1, 1).expand(3, 48, 64))
-    assert float(cu["alpha"].abs().max()) == 0.0 and float(cu["semantics"].abs().max()) == 0.0
+    assert float(cu["alpha"].detach().abs().max()) == 0.0 and float(cu["semantics"].detach().abs().max()) == 0.0
     for k, v in cu["grads"].items():
         assert v is None or float(v.abs().max()) == 0.0, k
 
@@ -210,8 +210,12 @@ def test_full_size_permutation_invariance(big_scene):
     gp = SyntheticGaussians(*[t[perm].contiguous() for t in g.tensors()])
     b = run_cuda(gp, cam, bg)
     assert torch.equal(a["radii"][perm], b["radii"])
+    # 1M float32 depths in [1,10) do collide now and then; a tie inside one tile composites in index
+    # order, which the shuffle changes.  Everything else must agree to rounding.
     for k in ("color", "semantics", "depth", "alpha"):
-        assert float((a[k] - b[k]).abs().max()) <= 1e-5, k
+        d = (a[k] - b[k]).abs().amax(dim=0)
+        assert float((d > 1e-5).float().mean()) < 1e-4, k
+        assert float(d.max()) < 5e-3, k
 
 
 def test_full_size_payload_linearity_and_euler(big_scene):
