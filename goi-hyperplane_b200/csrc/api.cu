@@ -133,6 +133,8 @@ static int validate(const goi_view* v, const goi_gaussians* g, bool need_opacity
     if (g->S > GOI_MAX_SEM) return fail(GOI_ERR_UNSUPPORTED, "S=%d semantic channels > GOI_MAX_SEM=%d", g->S, GOI_MAX_SEM);
     if ((v->width + TILE - 1) / TILE > 65535 || (v->height + TILE - 1) / TILE > 65535)
         return fail(GOI_ERR_UNSUPPORTED, "image too large for 16-bit tile coordinates");
+    if ((int64_t)g->P * (g->S > 4 ? g->S : 4) >= ((int64_t)1 << 31))
+        return fail(GOI_ERR_UNSUPPORTED, "P x S too large for 32-bit gradient indexing");
     if (g->P == 0) return GOI_OK;
     if (!g->means3D || (need_opacity && !g->opacities)) return fail(GOI_ERR_INVALID_ARG, "means3D/opacities are required");
     if ((g->shs == nullptr) == (g->colors_precomp == nullptr))

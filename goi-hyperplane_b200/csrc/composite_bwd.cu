@@ -54,8 +54,14 @@ __device__ __forceinline__ float group8_transpose_reduce(float (&v)[8], int lane
     return v[0];
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp: x = 1 - alpha is in [0.01, 1]
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int NS4, int BATCH>
-__global__ void __launch_bounds__(COMPOSITE_THREADS)
+__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 2 : 1))
 k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg, const float* __restrict__ out_alpha,
@@ -120,8 +126,8 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         if (dL_dpixalpha) g_alpha = dL_dpixalpha[pix];
     }
     const float bg_dot_dpixel = bg[0] * g_rgb[0] + bg[1] * g_rgb[1] + bg[2] * g_rgb[2];
-    const float ddelx_dx = 0.5 * W;
-    const float ddely_dy = 0.5 * H;
+    const float ddelx_dx = 0.5f * (float)W;         // reference: 0.5 * W (double, exact either way)
+    const float ddely_dy = 0.5f * (float)H;
 
     // ---- gsel[u][k] = pixel-gradient of payload value (vg*PPG + u) at pixel 4*pg + k of this warp: the
     //      4x PPG sub-block of the warp's 32 x NPROD gradient matrix this lane multiplies the weights with.
@@ -189,7 +195,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     //   u < PPG : payload value pv = vg*PPG + u  (pv < 3 colour | 3 depth | 4.. semantic pv-4)
     //   else    : geometry value gv = 2*vg + (u - PPG)  (0,1 mean2D.xy | 2,3,4 conic.x,.y,.w | 5 opacity)
     float* out_ptr[NBLK];
-    int out_stride[NBLK];
+    uint32_t out_stride[NBLK];
 #pragma unroll
     for (int k = 0; k < NBLK; ++k) {
         const int u = 8 * k + pg;
@@ -198,7 +204,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
             const int pv = vg * PPG + u;
             if (pv < 3) { out_ptr[k] = dL_dcolor + pv; out_stride[k] = 3; }
             else if (pv == 3) { out_ptr[k] = dL_ddepth; out_stride[k] = 1; }
-            else if (pv < NPROD && pv - 4 < S) { out_ptr[k] = dL_dsem + (pv - 4); out_stride[k] = S; }
+            else if (pv < NPROD && pv - 4 < S) { out_ptr[k] = dL_dsem + (pv - 4); out_stride[k] = (uint32_t)S; }
         } else if (u < VPG) {
             const int gv = 2 * vg + (u - PPG);
             if (gv < 2) { out_ptr[k] = dL_dmean2D + gv; out_stride[k] = 3; }
@@ -252,7 +258,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 if (!__any_sync(0xffffffffu, hit)) continue;
 
                 // ---- per-pixel values (branch-free; rejected lanes publish zeros) ----
-                const float inv = __frcp_rn(1.f - alpha);
+                const float inv = rcp_approx(1.f - alpha);
                 const float Tn = T * inv;                   // reference: T = T / (1 - alpha)
                 const float wgt = alpha * Tn;
                 const uint32_t ap = apay + j * (ROW * 16);
@@ -296,7 +302,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const float4 w4 = lds128(ar);
                 const float4 e0 = lds128(ar + grow0 * RSTRIDE * 4);
                 const float4 e1 = lds128(ar + grow1 * RSTRIDE * 4);
-                const int id = s_id[buf][j];
+                const uint32_t id = (uint32_t)s_id[buf][j];
 #pragma unroll
                 for (int k = 0; k < NBLK; ++k) {
                     float v[8];
@@ -311,7 +317,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                         else v[i] = 0.f;
                     }
                     const float r = group8_transpose_reduce(v, lane);
-                    if (out_ptr[k]) atomicAdd(out_ptr[k] + (size_t)id * out_stride[k], r);
+                    if (out_ptr[k]) atomicAdd(out_ptr[k] + (uint32_t)id * out_stride[k], r);
                 }
             }
         }

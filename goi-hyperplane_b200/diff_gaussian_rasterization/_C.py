@@ -106,6 +106,26 @@ SYMBOLS = {
     "goi_launch_count": (C.c_uint64, []),
 }
 GOI_NUM_STAGES = 9
+# Optional gradient arena: {name: preallocated tensor} for the parameter gradients "means3D", "sh",
+# "semantics", "opacities", "scales", "rotations", "colors_precomp", "cov3D_precomp".  When set, the backward
+# writes those gradients straight into the given tensors (e.g. slices of one flat all-reduce buffer, see
+# goi_b200/view_parallel.py) instead of fresh allocations -- no packing copy before the collective.
+grad_arena = None
+
+
+def set_grad_arena(arena):
+    global grad_arena
+    grad_arena = arena
+
+
+def _grad_out(name, shape, f32):
+    if grad_arena is not None and name in grad_arena:
+        t = grad_arena[name]
+        if t.numel() != int(torch.Size(shape).numel()) or not t.is_contiguous():
+            raise RuntimeError(f"grad arena entry {name!r} has {t.numel()} elements, expected shape {tuple(shape)}")
+        return t.view(shape)
+    return torch.empty(shape, **f32)
+
 last_num_rendered = 0      # R of the most recent forward on this thread (bench.py's roofline arithmetic)
 
 _lib = None
@@ -245,18 +265,18 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, 
         alphas = _f32(alphas, "alphas")
         keep += [gc, gs_, gd, ga, alphas]
         # fully written (or zero-initialised) inside the library: torch.empty, not torch.zeros
-        dL_dmeans3D = torch.empty((P, 3), **f32)
+        dL_dmeans3D = _grad_out("means3D", (P, 3), f32)
         dL_dmeans2D = torch.empty((P, 3), **f32)
-        dL_dcolors = torch.empty((P, 3), **f32)
-        dL_dsemantics = torch.empty((P, S), **f32)
+        dL_dcolors = _grad_out("colors_precomp", (P, 3), f32) if g.colors_precomp is not None else torch.empty((P, 3), **f32)
+        dL_dsemantics = _grad_out("semantics", (P, S), f32)
         dL_ddepths = torch.empty((P, 1), **f32)
         dL_dconic = torch.empty((P, 2, 2), **f32)
-        dL_dopacity = torch.empty((P, 1), **f32)
-        dL_dcov3D = torch.empty((P, 6), **f32)
+        dL_dopacity = _grad_out("opacities", (P, 1), f32)
         has_sh, has_scale = g.shs is not None, g.scales is not None
-        dL_dsh = torch.empty((P, M, 3), **f32) if has_sh else torch.zeros((P, M, 3), **f32)
-        dL_dscales = torch.empty((P, 3), **f32) if has_scale else torch.zeros((P, 3), **f32)
-        dL_drotations = torch.empty((P, 4), **f32) if has_scale else torch.zeros((P, 4), **f32)
+        dL_dcov3D = _grad_out("cov3D_precomp", (P, 6), f32) if not has_scale else torch.empty((P, 6), **f32)
+        dL_dsh = _grad_out("sh", (P, M, 3), f32) if has_sh else torch.zeros((P, M, 3), **f32)
+        dL_dscales = _grad_out("scales", (P, 3), f32) if has_scale else torch.zeros((P, 3), **f32)
+        dL_drotations = _grad_out("rotations", (P, 4), f32) if has_scale else torch.zeros((P, 4), **f32)
         if P != 0:
             gin = goi_bwd_in(_ptr(gc), _ptr(gs_), _ptr(gd), _ptr(ga), _ptr(alphas), _ptr(radii))
             gout = goi_bwd_out(_ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors),

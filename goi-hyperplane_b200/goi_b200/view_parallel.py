@@ -51,6 +51,45 @@ class FlatGradBuffer:
         return [self.flat[o:o + n].view(p.shape) for (o, n), p in zip(self.slices, self.params)]
 
 
+class GradArena:
+    """Flat f32 buffer whose slices RECEIVE the rasterizer's parameter gradients directly (the C ABI takes
+    caller-owned output pointers), so one view per rank per step needs neither a zero fill, nor autograd's
+    accumulate-add, nor a packing copy before the all-reduce.
+
+    `named_params` maps the binding's gradient names ("means3D", "sh", "semantics", "opacities", "scales",
+    "rotations", ...) to the parameter tensors.  Use as a context manager around the backward call; after it,
+    `p.grad` of every parameter is the arena slice (set `p.grad = None` before each step)."""
+
+    def __init__(self, named_params: dict):
+        self.named = dict(named_params)
+        ps = list(self.named.values())
+        dev = ps[0].device
+        self.flat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+        self.slots, off = {}, 0
+        for name, p in self.named.items():
+            self.slots[name] = self.flat[off:off + p.numel()]
+            off += p.numel()
+
+    def __enter__(self):
+        from diff_gaussian_rasterization import _C
+        _C.set_grad_arena(self.slots)
+        return self
+
+    def __exit__(self, *exc):
+        from diff_gaussian_rasterization import _C
+        _C.set_grad_arena(None)
+        return False
+
+    def clear_grads(self):
+        for p in self.named.values():
+            p.grad = None
+
+    def all_reduce(self, async_op: bool = False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return None
+
+
 def accumulate_views(views: Iterable, params: Sequence[torch.Tensor], loss_fn: Callable, flat: FlatGradBuffer | None = None,
                      rank: int | None = None, world: int | None = None):
     """Render this rank's share of `views`, back-propagate `loss_fn(view)` for each, and all-reduce.
