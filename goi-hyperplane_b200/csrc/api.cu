@@ -143,6 +143,7 @@ static int validate(const goi_view* v, const goi_gaussians* g, bool need_opacity
         ((g->scales != nullptr || g->rotations != nullptr) && g->cov3D_precomp != nullptr))
         return fail(GOI_ERR_INVALID_ARG, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
     if (g->S > 0 && !g->semantics) return fail(GOI_ERR_INVALID_ARG, "S > 0 but semantics is NULL");
+    if (g->shs && g->M > 16) return fail(GOI_ERR_UNSUPPORTED, "M=%d SH coefficients per channel > 16", g->M);
     if (g->shs && (g->M < (v->sh_degree + 1) * (v->sh_degree + 1) || v->sh_degree < 0 || v->sh_degree > 3))
         return fail(GOI_ERR_INVALID_ARG, "sh_degree %d needs %d coefficients, M=%d", v->sh_degree,
                     (v->sh_degree + 1) * (v->sh_degree + 1), g->M);

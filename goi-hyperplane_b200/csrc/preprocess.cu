@@ -103,7 +103,60 @@ __device__ __forceinline__ Cov2DSetup cov2d_setup(const float3& mean, float fx, 
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_preprocess_fwd(
+constexpr int PRE_WARPS = 4;          // 128-thread blocks: 4 warps x (32 Gaussians x 3M SH floats) of shared memory
+constexpr int PRE_ROWSTRIDE = 49;     // 48 floats per SH row + 1: per-thread row walks are bank-conflict-free
+
+// Coalesced move of a warp's 32 x rowlen SH block between global memory and a shared-memory tile whose rows
+// are padded to PRE_ROWSTRIDE floats.  Fast path (rowlen == 48, 16-byte aligned): 12 independent LDG.128 /
+// STG.128 per lane in flight; general path: scalar.
+__device__ __forceinline__ void sh_tile_load(float* tile, const float* __restrict__ src, int rows, int rowlen, int lane)
+{
+    if (rowlen == 48 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        float4 v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int f = lane + 32 * k;
+            v[k] = (f < rows * 12) ? src4[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int f = lane + 32 * k;
+            float* d = tile + (f / 12) * PRE_ROWSTRIDE + (f % 12) * 4;
+            d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+        }
+    } else {
+        int row = 0, col = lane;
+        while (col >= rowlen) { col -= rowlen; ++row; }
+        for (int i = lane; i < rows * rowlen; i += 32) {
+            tile[row * PRE_ROWSTRIDE + col] = src[i];
+            col += 32;
+            while (col >= rowlen) { col -= rowlen; ++row; }
+        }
+    }
+}
+__device__ __forceinline__ void sh_tile_store(float* __restrict__ dst, const float* tile, int rows, int rowlen, int lane)
+{
+    if (rowlen == 48 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        float4* dst4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int f = lane + 32 * k;
+            const float* d = tile + (f / 12) * PRE_ROWSTRIDE + (f % 12) * 4;
+            if (f < rows * 12) dst4[f] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    } else {
+        int r = 0, col = lane;
+        while (col >= rowlen) { col -= rowlen; ++r; }
+        for (int i = lane; i < rows * rowlen; i += 32) {
+            dst[i] = tile[r * PRE_ROWSTRIDE + col];
+            col += 32;
+            while (col >= rowlen) { col -= rowlen; ++r; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_preprocess_fwd(
     int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
     const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
@@ -112,104 +165,130 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     int32_t* __restrict__ radii, float4* __restrict__ geo, float4* __restrict__ rgbd, float* __restrict__ cov3Ds,
     uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rect, Meta* meta)
 {
+    // One warp = 32 consecutive Gaussians.  The per-Gaussian geometry is computed first; the SH rows of the
+    // whole warp (32 x 3M contiguous floats) are then staged through shared memory with coalesced loads,
+    // because a per-thread walk over its own 192-byte row touches 32 different sectors per instruction.
+    __shared__ float s_sh[PRE_WARPS][32 * PRE_ROWSTRIDE];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool visible = false;
+    float3 p_orig = make_float3(0.f, 0.f, 0.f);
+    float2 point_image = make_float2(0.f, 0.f);
+    float3 conic = make_float3(0.f, 0.f, 0.f);
+    float depth = 0.f;
+    int max_radius = 0, minx = 0, miny = 0, maxx = 0, maxy = 0;
 
-    radii[idx] = 0;
-    tiles_touched[idx] = 0;
+    do {
+        if (idx >= P) break;
+        radii[idx] = 0;
+        tiles_touched[idx] = 0;
 
-    // in_frustum, auxiliary.h:139-164
-    const float3 p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
-    const float3 p_view = xform4x3(p_orig, viewmatrix);
-    if (p_view.z <= 0.2f) {
-        if (prefiltered) meta->prefilter_violation = 1;   // the reference printf()s and __trap()s here
-        return;
-    }
-    const float4 p_hom = xform4x4(p_orig, projmatrix);
-    const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-    const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+        // in_frustum, auxiliary.h:139-164
+        p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+        const float3 p_view = xform4x3(p_orig, viewmatrix);
+        if (p_view.z <= 0.2f) {
+            if (prefiltered) meta->prefilter_violation = 1;   // the reference printf()s and __trap()s here
+            break;
+        }
+        depth = p_view.z;
+        const float4 p_hom = xform4x4(p_orig, projmatrix);
+        const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
 
-    // computeCov3D, forward.cu:118-152
-    float c3[6];
-    if (cov3D_precomp != nullptr) {
+        // computeCov3D, forward.cu:118-152
+        float c3[6];
+        if (cov3D_precomp != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) c3[i] = cov3D_precomp[6 * idx + i];
-    } else {
-        M3 S = m3_make(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
-        S.m[0][0] = scale_modifier * scales[3 * idx + 0];
-        S.m[1][1] = scale_modifier * scales[3 * idx + 1];
-        S.m[2][2] = scale_modifier * scales[3 * idx + 2];
-        const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
-        const M3 R = quat_R(q);
-        const M3 Mm = m3_mul(S, R);
-        const M3 Sigma = m3_mul(m3_t(Mm), Mm);
-        c3[0] = Sigma.m[0][0]; c3[1] = Sigma.m[0][1]; c3[2] = Sigma.m[0][2];
-        c3[3] = Sigma.m[1][1]; c3[4] = Sigma.m[1][2]; c3[5] = Sigma.m[2][2];
+            for (int i = 0; i < 6; ++i) c3[i] = cov3D_precomp[6 * idx + i];
+        } else {
+            M3 S = m3_make(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
+            S.m[0][0] = scale_modifier * scales[3 * idx + 0];
+            S.m[1][1] = scale_modifier * scales[3 * idx + 1];
+            S.m[2][2] = scale_modifier * scales[3 * idx + 2];
+            const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+            const M3 R = quat_R(q);
+            const M3 Mm = m3_mul(S, R);
+            const M3 Sigma = m3_mul(m3_t(Mm), Mm);
+            c3[0] = Sigma.m[0][0]; c3[1] = Sigma.m[0][1]; c3[2] = Sigma.m[0][2];
+            c3[3] = Sigma.m[1][1]; c3[4] = Sigma.m[1][2]; c3[5] = Sigma.m[2][2];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) cov3Ds[6 * idx + i] = c3[i];
-    }
+            for (int i = 0; i < 6; ++i) cov3Ds[6 * idx + i] = c3[i];
+        }
 
-    // computeCov2D, forward.cu:74-113
-    Cov2DSetup cs = cov2d_setup(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, c3, viewmatrix);
-    cs.cov.m[0][0] += 0.3f;
-    cs.cov.m[1][1] += 0.3f;
-    const float3 cov = make_float3(cs.cov.m[0][0], cs.cov.m[0][1], cs.cov.m[1][1]);
+        // computeCov2D, forward.cu:74-113
+        Cov2DSetup cs = cov2d_setup(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, c3, viewmatrix);
+        cs.cov.m[0][0] += 0.3f;
+        cs.cov.m[1][1] += 0.3f;
+        const float3 cov = make_float3(cs.cov.m[0][0], cs.cov.m[0][1], cs.cov.m[1][1]);
 
-    // invert, forward.cu:219-223
-    const float det = (cov.x * cov.z - cov.y * cov.y);
-    if (det == 0.0f) return;
-    const float det_inv = 1.f / det;
-    const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+        // invert, forward.cu:219-223
+        const float det = (cov.x * cov.z - cov.y * cov.y);
+        if (det == 0.0f) break;
+        const float det_inv = 1.f / det;
+        conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
 
-    // extent + tile rectangle, forward.cu:229-237 and auxiliary.h:46-56
-    const float mid = 0.5f * (cov.x + cov.z);
-    const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-    const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-    const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
-    const float2 point_image = make_float2(ndc2pix(p_proj.x, W), ndc2pix(p_proj.y, H));
-    const int max_radius = (int)my_radius;
-    const int minx = min(gx, max(0, (int)((point_image.x - max_radius) / TILE)));
-    const int miny = min(gy, max(0, (int)((point_image.y - max_radius) / TILE)));
-    const int maxx = min(gx, max(0, (int)((point_image.x + max_radius + TILE - 1) / TILE)));
-    const int maxy = min(gy, max(0, (int)((point_image.y + max_radius + TILE - 1) / TILE)));
-    if ((maxx - minx) * (maxy - miny) == 0) return;
+        // extent + tile rectangle, forward.cu:229-237 and auxiliary.h:46-56
+        const float mid = 0.5f * (cov.x + cov.z);
+        const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+        point_image = make_float2(ndc2pix(p_proj.x, W), ndc2pix(p_proj.y, H));
+        max_radius = (int)my_radius;
+        minx = min(gx, max(0, (int)((point_image.x - max_radius) / TILE)));
+        miny = min(gy, max(0, (int)((point_image.y - max_radius) / TILE)));
+        maxx = min(gx, max(0, (int)((point_image.x + max_radius + TILE - 1) / TILE)));
+        maxy = min(gy, max(0, (int)((point_image.y + max_radius + TILE - 1) / TILE)));
+        if ((maxx - minx) * (maxy - miny) == 0) break;
+        visible = true;
+    } while (0);
 
     // colour: SH -> RGB (forward.cu:20-71) or precomputed
-    float3 rgb;
+    float3 rgb = make_float3(0.f, 0.f, 0.f);
     if (colors_precomp == nullptr) {
-        float3 dir = make_float3(p_orig.x - cam_pos[0], p_orig.y - cam_pos[1], p_orig.z - cam_pos[2]);
-        const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-        dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
-        const float* sh = shs + (size_t)idx * M * 3;
-        float res[3];
+        float* tile = s_sh[warp];
+        const int rowlen = 3 * M;
+        if (__any_sync(0xffffffffu, visible)) {
+            const int base = blockIdx.x * blockDim.x + warp * 32;
+            const int rows = min(32, P - base);
+            sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
+            __syncwarp();
+        }
+        if (visible) {
+            float3 dir = make_float3(p_orig.x - cam_pos[0], p_orig.y - cam_pos[1], p_orig.z - cam_pos[2]);
+            const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+            dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
+            const float* sh = tile + lane * PRE_ROWSTRIDE;
+            float res[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float r = kSH_C0 * sh[c];
-            if (D > 0) {
-                const float x = dir.x, y = dir.y, z = dir.z;
-                r = r - kSH_C1 * y * sh[3 + c] + kSH_C1 * z * sh[6 + c] - kSH_C1 * x * sh[9 + c];
-                if (D > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z;
-                    const float xy = x * y, yz = y * z, xz = x * z;
-                    r = r + kSH_C2[0] * xy * sh[12 + c] + kSH_C2[1] * yz * sh[15 + c] +
-                        kSH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + kSH_C2[3] * xz * sh[21 + c] +
-                        kSH_C2[4] * (xx - yy) * sh[24 + c];
-                    if (D > 2) {
-                        r = r + kSH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + kSH_C3[1] * xy * z * sh[30 + c] +
-                            kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                            kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                            kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + kSH_C3[5] * z * (xx - yy) * sh[42 + c] +
-                            kSH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+            for (int c = 0; c < 3; ++c) {
+                float r = kSH_C0 * sh[c];
+                if (D > 0) {
+                    const float x = dir.x, y = dir.y, z = dir.z;
+                    r = r - kSH_C1 * y * sh[3 + c] + kSH_C1 * z * sh[6 + c] - kSH_C1 * x * sh[9 + c];
+                    if (D > 1) {
+                        const float xx = x * x, yy = y * y, zz = z * z;
+                        const float xy = x * y, yz = y * z, xz = x * z;
+                        r = r + kSH_C2[0] * xy * sh[12 + c] + kSH_C2[1] * yz * sh[15 + c] +
+                            kSH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + kSH_C2[3] * xz * sh[21 + c] +
+                            kSH_C2[4] * (xx - yy) * sh[24 + c];
+                        if (D > 2) {
+                            r = r + kSH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + kSH_C3[1] * xy * z * sh[30 + c] +
+                                kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
+                                kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
+                                kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + kSH_C3[5] * z * (xx - yy) * sh[42 + c] +
+                                kSH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                        }
                     }
                 }
+                res[c] = r + 0.5f;
             }
-            res[c] = r + 0.5f;
+            clamped[idx] = (uint8_t)((res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0));
+            rgb = make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
         }
-        clamped[idx] = (uint8_t)((res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0));
-        rgb = make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
-    } else {
+    } else if (visible) {
         rgb = make_float3(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]);
     }
+    if (!visible) return;
 
     const float opacity = opacities[idx];
     // power_cut: a pair with power < power_cut has opacity*exp(power) < 1/255 with margin, so the
@@ -220,7 +299,7 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     radii[idx] = max_radius;
     geo[2 * idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
     geo[2 * idx + 1] = make_float4(conic.z, opacity, power_cut, 0.f);
-    rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, p_view.z);
+    rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, depth);
     rect[idx] = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
     // Instances = tiles of the reference rectangle that can actually reach alpha >= 1/255 (goi_cull.cuh).
     // k_emit_keys repeats exactly this test, so the prefix sum and the emission agree.
@@ -239,7 +318,7 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
     const float focal_x = v.width / (2.0f * v.tan_fovx);
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
     cudaMemsetAsync(gs.meta, 0, sizeof(Meta), st);
-    k_preprocess_fwd<<<(P + 255) / 256, 256, 0, st>>>(
+    k_preprocess_fwd<<<(P + 127) / 128, 128, 0, st>>>(
         P, v.sh_degree, g.M, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
         g.cov3D_precomp, g.colors_precomp, v.viewmatrix, v.projmatrix, v.cam_pos, v.width, v.height,
         v.tan_fovx, v.tan_fovy, focal_x, focal_y, gx, gy, v.prefiltered, radii, gs.geo, gs.rgbd, gs.cov3D,
@@ -252,7 +331,7 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
 // Per-Gaussian backward: d(conic) -> d(cov2D) -> d(cov3D), d(mean) through the EWA Jacobian, the
 // projection, the depth and the SH view direction; d(cov3D) -> d(scale), d(quaternion).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_preprocess_bwd(
+__global__ void __launch_bounds__(128) k_preprocess_bwd(
     int P, int D, int M, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
     const float* __restrict__ rotations, float scale_modifier, const float* __restrict__ cov3Ds,
@@ -263,226 +342,248 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
     float* __restrict__ dL_dmeans, float* __restrict__ dL_dcov, float* __restrict__ dL_dsh,
     float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
 {
+    // One warp = 32 consecutive Gaussians; their SH rows (and the dL_dsh rows) are 32 x 3M contiguous floats
+    // and move through one shared-memory tile with fully coalesced global accesses.
+    __shared__ float s_sh[PRE_WARPS][32 * PRE_ROWSTRIDE];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    if (!(radii[idx] > 0)) {
-        // rows the reference leaves at their torch::zeros value
-        dL_dmeans[3 * idx] = 0.f; dL_dmeans[3 * idx + 1] = 0.f; dL_dmeans[3 * idx + 2] = 0.f;
-        if (dL_dcov) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_range = idx < P;
+    const bool active = in_range && (radii[idx] > 0);
+    float* tile = s_sh[warp];
+    const int rowlen = 3 * M;
+    const int base = blockIdx.x * blockDim.x + warp * 32;
+    const int rows = max(0, min(32, P - base));
+
+    if (shs != nullptr && __any_sync(0xffffffffu, active)) {
+        sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
+    }
+    __syncwarp();
+
+    float3 gmean = make_float3(0.f, 0.f, 0.f);
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float3 mean = make_float3(0.f, 0.f, 0.f);
+    if (active) {
+        // ---- computeCov2DCUDA, backward.cu:144-274 ----
+        mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+        float c3[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) dL_dcov[6 * idx + i] = 0.f;
+        for (int i = 0; i < 6; ++i) c3[i] = cov3Ds[6 * idx + i];
+        const float3 dL_dconic = make_float3(dL_dconics[4 * idx], dL_dconics[4 * idx + 1], dL_dconics[4 * idx + 3]);
+        Cov2DSetup cs = cov2d_setup(mean, h_x, h_y, tan_fovx, tan_fovy, c3, view);
+        const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
+        const float x_grad_mul = cs.txtz < -limx || cs.txtz > limx ? 0 : 1;
+        const float y_grad_mul = cs.tytz < -limy || cs.tytz > limy ? 0 : 1;
+        const float3 t = cs.t;
+        const M3& T = cs.T; const M3& Vrk = cs.Vrk; const M3& Wm = cs.W;
+
+        const float a = cs.cov.m[0][0] += 0.3f;
+        const float b = cs.cov.m[0][1];
+        const float c = cs.cov.m[1][1] += 0.3f;
+
+        const float denom = a * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+            dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+
+            dcov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+            dcov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+            dcov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+            dcov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
+            dcov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
+            dcov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
         }
-        if (dL_dsh) for (int i = 0; i < 3 * M; ++i) dL_dsh[(size_t)idx * 3 * M + i] = 0.f;
-        if (dL_dscale) { dL_dscale[3 * idx] = 0.f; dL_dscale[3 * idx + 1] = 0.f; dL_dscale[3 * idx + 2] = 0.f; }
-        if (dL_drot) *reinterpret_cast<float4*>(dL_drot + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
+
+        const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
+                              (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
+        const float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da +
+                              (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
+        const float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da +
+                              (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
+        const float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc +
+                              (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
+        const float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc +
+                              (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
+        const float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc +
+                              (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
+
+        const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
+        const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
+        const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
+        const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
+
+        const float tz = 1.f / t.z;
+        const float tz2 = tz * tz;
+        const float tz3 = tz2 * tz;
+
+        const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+        const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+        const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+
+        // transformVec4x3Transpose, auxiliary.h:89-97
+        gmean = make_float3(view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz,
+                            view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
+                            view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz);
+
+        // ---- preprocessCUDA (backward), backward.cu:346-412 ----
+        const float4 m_hom = xform4x4(mean, proj);
+        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+        const float g2x = dL_dmean2D[3 * idx], g2y = dL_dmean2D[3 * idx + 1];
+        float3 dm;
+        dm.x = (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
+        dm.y = (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
+        dm.z = (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+        gmean.x += dm.x; gmean.y += dm.y; gmean.z += dm.z;
+
+        const float gdepth = dL_ddepth[idx];
+        const float mul3 = view[2] * mean.x + view[6] * mean.y + view[10] * mean.z + view[14];
+        float3 dm2;
+        dm2.x = (view[2] - view[3] * mul3) * gdepth;
+        dm2.y = (view[6] - view[7] * mul3) * gdepth;
+        dm2.z = (view[10] - view[11] * mul3) * gdepth;
+        gmean.x += dm2.x; gmean.y += dm2.y; gmean.z += dm2.z;
     }
 
-    // ---- computeCov2DCUDA, backward.cu:144-274 ----
-    const float3 mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
-    float c3[6];
+    // ---- computeColorFromSH (backward), backward.cu:20-139 ----
+    if (shs != nullptr) {
+        float* row = tile + lane * PRE_ROWSTRIDE;
+        float coef[16];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) c3[i] = cov3Ds[6 * idx + i];
-    const float3 dL_dconic = make_float3(dL_dconics[4 * idx], dL_dconics[4 * idx + 1], dL_dconics[4 * idx + 3]);
-    Cov2DSetup cs = cov2d_setup(mean, h_x, h_y, tan_fovx, tan_fovy, c3, view);
-    const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
-    const float x_grad_mul = cs.txtz < -limx || cs.txtz > limx ? 0 : 1;
-    const float y_grad_mul = cs.tytz < -limy || cs.tytz > limy ? 0 : 1;
-    const float3 t = cs.t;
-    const M3& T = cs.T; const M3& Vrk = cs.Vrk; const M3& Wm = cs.W;
-
-    const float a = cs.cov.m[0][0] += 0.3f;
-    const float b = cs.cov.m[0][1];
-    const float c = cs.cov.m[1][1] += 0.3f;
-
-    const float denom = a * c - b * b;
-    float dL_da = 0, dL_db = 0, dL_dc = 0;
-    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    float dcov[6];
-    if (denom2inv != 0) {
-        dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
-        dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
-        dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
-
-        dcov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
-        dcov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
-        dcov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
-        dcov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
-        dcov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
-        dcov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
-    } else {
+        for (int k = 0; k < 16; ++k) coef[k] = 0.f;
+        float dRGB[3] = {0.f, 0.f, 0.f};
+        if (active) {
+            const float3 dir_orig = make_float3(mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]);
+            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+            const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+            const float* sh = row;
+            const uint8_t cl = clamped[idx];
+            dRGB[0] = dL_dcolor[3 * idx]; dRGB[1] = dL_dcolor[3 * idx + 1]; dRGB[2] = dL_dcolor[3 * idx + 2];
+            dRGB[0] *= (cl & 1) ? 0 : 1;
+            dRGB[1] *= (cl & 2) ? 0 : 1;
+            dRGB[2] *= (cl & 4) ? 0 : 1;
+            float dx3[3] = {0, 0, 0}, dy3[3] = {0, 0, 0}, dz3[3] = {0, 0, 0};
+#define GOI_SH(k, c) sh[3 * (k) + (c)]
+            coef[0] = kSH_C0;
+            if (D > 0) {
+                coef[1] = -kSH_C1 * y;
+                coef[2] = kSH_C1 * z;
+                coef[3] = -kSH_C1 * x;
 #pragma unroll
-        for (int i = 0; i < 6; i++) dcov[i] = 0;
+                for (int cc = 0; cc < 3; ++cc) {
+                    dx3[cc] = -kSH_C1 * GOI_SH(3, cc);
+                    dy3[cc] = -kSH_C1 * GOI_SH(1, cc);
+                    dz3[cc] = kSH_C1 * GOI_SH(2, cc);
+                }
+                if (D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z;
+                    const float xy = x * y, yz = y * z, xz = x * z;
+                    coef[4] = kSH_C2[0] * xy;
+                    coef[5] = kSH_C2[1] * yz;
+                    coef[6] = kSH_C2[2] * (2.f * zz - xx - yy);
+                    coef[7] = kSH_C2[3] * xz;
+                    coef[8] = kSH_C2[4] * (xx - yy);
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        dx3[cc] += kSH_C2[0] * y * GOI_SH(4, cc) + kSH_C2[2] * 2.f * -x * GOI_SH(6, cc) + kSH_C2[3] * z * GOI_SH(7, cc) + kSH_C2[4] * 2.f * x * GOI_SH(8, cc);
+                        dy3[cc] += kSH_C2[0] * x * GOI_SH(4, cc) + kSH_C2[1] * z * GOI_SH(5, cc) + kSH_C2[2] * 2.f * -y * GOI_SH(6, cc) + kSH_C2[4] * 2.f * -y * GOI_SH(8, cc);
+                        dz3[cc] += kSH_C2[1] * y * GOI_SH(5, cc) + kSH_C2[2] * 2.f * 2.f * z * GOI_SH(6, cc) + kSH_C2[3] * x * GOI_SH(7, cc);
+                    }
+                    if (D > 2) {
+                        coef[9] = kSH_C3[0] * y * (3.f * xx - yy);
+                        coef[10] = kSH_C3[1] * xy * z;
+                        coef[11] = kSH_C3[2] * y * (4.f * zz - xx - yy);
+                        coef[12] = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                        coef[13] = kSH_C3[4] * x * (4.f * zz - xx - yy);
+                        coef[14] = kSH_C3[5] * z * (xx - yy);
+                        coef[15] = kSH_C3[6] * x * (xx - 3.f * yy);
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            dx3[cc] += (kSH_C3[0] * GOI_SH(9, cc) * 3.f * 2.f * xy + kSH_C3[1] * GOI_SH(10, cc) * yz +
+                                        kSH_C3[2] * GOI_SH(11, cc) * -2.f * xy + kSH_C3[3] * GOI_SH(12, cc) * -3.f * 2.f * xz +
+                                        kSH_C3[4] * GOI_SH(13, cc) * (-3.f * xx + 4.f * zz - yy) +
+                                        kSH_C3[5] * GOI_SH(14, cc) * 2.f * xz + kSH_C3[6] * GOI_SH(15, cc) * 3.f * (xx - yy));
+                            dy3[cc] += (kSH_C3[0] * GOI_SH(9, cc) * 3.f * (xx - yy) + kSH_C3[1] * GOI_SH(10, cc) * xz +
+                                        kSH_C3[2] * GOI_SH(11, cc) * (-3.f * yy + 4.f * zz - xx) +
+                                        kSH_C3[3] * GOI_SH(12, cc) * -3.f * 2.f * yz + kSH_C3[4] * GOI_SH(13, cc) * -2.f * xy +
+                                        kSH_C3[5] * GOI_SH(14, cc) * -2.f * yz + kSH_C3[6] * GOI_SH(15, cc) * -3.f * 2.f * xy);
+                            dz3[cc] += (kSH_C3[1] * GOI_SH(10, cc) * xy + kSH_C3[2] * GOI_SH(11, cc) * 4.f * 2.f * yz +
+                                        kSH_C3[3] * GOI_SH(12, cc) * 3.f * (2.f * zz - xx - yy) +
+                                        kSH_C3[4] * GOI_SH(13, cc) * 4.f * 2.f * xz + kSH_C3[5] * GOI_SH(14, cc) * (xx - yy));
+                        }
+                    }
+                }
+            }
+#undef GOI_SH
+            const float3 dL_ddir = make_float3(dx3[0] * dRGB[0] + dx3[1] * dRGB[1] + dx3[2] * dRGB[2],
+                                               dy3[0] * dRGB[0] + dy3[1] * dRGB[1] + dy3[2] * dRGB[2],
+                                               dz3[0] * dRGB[0] + dz3[1] * dRGB[1] + dz3[2] * dRGB[2]);
+            // dnormvdv, auxiliary.h:107-117
+            const float3 v = dir_orig;
+            const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+            const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            gmean.x += ((+sum2 - v.x * v.x) * dL_ddir.x - v.y * v.x * dL_ddir.y - v.z * v.x * dL_ddir.z) * invsum32;
+            gmean.y += (-v.x * v.y * dL_ddir.x + (sum2 - v.y * v.y) * dL_ddir.y - v.z * v.y * dL_ddir.z) * invsum32;
+            gmean.z += (-v.x * v.z * dL_ddir.x - v.y * v.z * dL_ddir.y + (sum2 - v.z * v.z) * dL_ddir.z) * invsum32;
+        }
+        // every SH read of this row is done: overwrite the row with dL/dSH = coefficient * dL/dRGB (zeros for
+        // culled Gaussians and for coefficients above the active degree, like the reference's zero fill)
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < M) {
+                row[3 * k + 0] = coef[k] * dRGB[0];
+                row[3 * k + 1] = coef[k] * dRGB[1];
+                row[3 * k + 2] = coef[k] * dRGB[2];
+            }
+        __syncwarp();
+        sh_tile_store(dL_dsh + (size_t)base * rowlen, tile, rows, rowlen, lane);
     }
+    if (!in_range) return;
+    dL_dmeans[3 * idx] = gmean.x; dL_dmeans[3 * idx + 1] = gmean.y; dL_dmeans[3 * idx + 2] = gmean.z;
     if (dL_dcov) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) dL_dcov[6 * idx + i] = dcov[i];
     }
 
-    const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
-                          (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
-    const float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da +
-                          (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
-    const float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da +
-                          (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
-    const float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc +
-                          (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
-    const float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc +
-                          (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
-    const float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc +
-                          (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
-
-    const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
-    const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
-    const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
-    const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
-
-    const float tz = 1.f / t.z;
-    const float tz2 = tz * tz;
-    const float tz3 = tz2 * tz;
-
-    const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
-    const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
-    const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
-
-    // transformVec4x3Transpose, auxiliary.h:89-97
-    float3 gmean = make_float3(view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz,
-                               view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
-                               view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz);
-
-    // ---- preprocessCUDA (backward), backward.cu:346-412 ----
-    const float4 m_hom = xform4x4(mean, proj);
-    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-    const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
-    const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-    const float g2x = dL_dmean2D[3 * idx], g2y = dL_dmean2D[3 * idx + 1];
-    float3 dm;
-    dm.x = (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
-    dm.y = (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
-    dm.z = (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
-    gmean.x += dm.x; gmean.y += dm.y; gmean.z += dm.z;
-
-    const float gdepth = dL_ddepth[idx];
-    const float mul3 = view[2] * mean.x + view[6] * mean.y + view[10] * mean.z + view[14];
-    float3 dm2;
-    dm2.x = (view[2] - view[3] * mul3) * gdepth;
-    dm2.y = (view[6] - view[7] * mul3) * gdepth;
-    dm2.z = (view[10] - view[11] * mul3) * gdepth;
-    gmean.x += dm2.x; gmean.y += dm2.y; gmean.z += dm2.z;
-
-    // ---- computeColorFromSH (backward), backward.cu:20-139 ----
-    if (shs != nullptr) {
-        const float3 dir_orig = make_float3(mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]);
-        const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-        const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-        const float* sh = shs + (size_t)idx * M * 3;
-        float* dsh = dL_dsh + (size_t)idx * M * 3;
-        const uint8_t cl = clamped[idx];
-        float dRGB[3] = {dL_dcolor[3 * idx], dL_dcolor[3 * idx + 1], dL_dcolor[3 * idx + 2]};
-        dRGB[0] *= (cl & 1) ? 0 : 1;
-        dRGB[1] *= (cl & 2) ? 0 : 1;
-        dRGB[2] *= (cl & 4) ? 0 : 1;
-        float dx3[3] = {0, 0, 0}, dy3[3] = {0, 0, 0}, dz3[3] = {0, 0, 0};
-#define GOI_SETSH(k, coef) { const float cf_ = (coef); dsh[3 * (k)] = cf_ * dRGB[0]; dsh[3 * (k) + 1] = cf_ * dRGB[1]; dsh[3 * (k) + 2] = cf_ * dRGB[2]; }
-#define GOI_SH(k, c) sh[3 * (k) + (c)]
-        GOI_SETSH(0, kSH_C0);
-        if (D > 0) {
-            GOI_SETSH(1, -kSH_C1 * y);
-            GOI_SETSH(2, kSH_C1 * z);
-            GOI_SETSH(3, -kSH_C1 * x);
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                dx3[cc] = -kSH_C1 * GOI_SH(3, cc);
-                dy3[cc] = -kSH_C1 * GOI_SH(1, cc);
-                dz3[cc] = kSH_C1 * GOI_SH(2, cc);
-            }
-            if (D > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                GOI_SETSH(4, kSH_C2[0] * xy);
-                GOI_SETSH(5, kSH_C2[1] * yz);
-                GOI_SETSH(6, kSH_C2[2] * (2.f * zz - xx - yy));
-                GOI_SETSH(7, kSH_C2[3] * xz);
-                GOI_SETSH(8, kSH_C2[4] * (xx - yy));
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    dx3[cc] += kSH_C2[0] * y * GOI_SH(4, cc) + kSH_C2[2] * 2.f * -x * GOI_SH(6, cc) + kSH_C2[3] * z * GOI_SH(7, cc) + kSH_C2[4] * 2.f * x * GOI_SH(8, cc);
-                    dy3[cc] += kSH_C2[0] * x * GOI_SH(4, cc) + kSH_C2[1] * z * GOI_SH(5, cc) + kSH_C2[2] * 2.f * -y * GOI_SH(6, cc) + kSH_C2[4] * 2.f * -y * GOI_SH(8, cc);
-                    dz3[cc] += kSH_C2[1] * y * GOI_SH(5, cc) + kSH_C2[2] * 2.f * 2.f * z * GOI_SH(6, cc) + kSH_C2[3] * x * GOI_SH(7, cc);
-                }
-                if (D > 2) {
-                    GOI_SETSH(9, kSH_C3[0] * y * (3.f * xx - yy));
-                    GOI_SETSH(10, kSH_C3[1] * xy * z);
-                    GOI_SETSH(11, kSH_C3[2] * y * (4.f * zz - xx - yy));
-                    GOI_SETSH(12, kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                    GOI_SETSH(13, kSH_C3[4] * x * (4.f * zz - xx - yy));
-                    GOI_SETSH(14, kSH_C3[5] * z * (xx - yy));
-                    GOI_SETSH(15, kSH_C3[6] * x * (xx - 3.f * yy));
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        dx3[cc] += (kSH_C3[0] * GOI_SH(9, cc) * 3.f * 2.f * xy + kSH_C3[1] * GOI_SH(10, cc) * yz +
-                                    kSH_C3[2] * GOI_SH(11, cc) * -2.f * xy + kSH_C3[3] * GOI_SH(12, cc) * -3.f * 2.f * xz +
-                                    kSH_C3[4] * GOI_SH(13, cc) * (-3.f * xx + 4.f * zz - yy) +
-                                    kSH_C3[5] * GOI_SH(14, cc) * 2.f * xz + kSH_C3[6] * GOI_SH(15, cc) * 3.f * (xx - yy));
-                        dy3[cc] += (kSH_C3[0] * GOI_SH(9, cc) * 3.f * (xx - yy) + kSH_C3[1] * GOI_SH(10, cc) * xz +
-                                    kSH_C3[2] * GOI_SH(11, cc) * (-3.f * yy + 4.f * zz - xx) +
-                                    kSH_C3[3] * GOI_SH(12, cc) * -3.f * 2.f * yz + kSH_C3[4] * GOI_SH(13, cc) * -2.f * xy +
-                                    kSH_C3[5] * GOI_SH(14, cc) * -2.f * yz + kSH_C3[6] * GOI_SH(15, cc) * -3.f * 2.f * xy);
-                        dz3[cc] += (kSH_C3[1] * GOI_SH(10, cc) * xy + kSH_C3[2] * GOI_SH(11, cc) * 4.f * 2.f * yz +
-                                    kSH_C3[3] * GOI_SH(12, cc) * 3.f * (2.f * zz - xx - yy) +
-                                    kSH_C3[4] * GOI_SH(13, cc) * 4.f * 2.f * xz + kSH_C3[5] * GOI_SH(14, cc) * (xx - yy));
-                    }
-                }
-            }
-        }
-        // coefficients above the active degree keep the reference's zero fill
-        for (int k = (D + 1) * (D + 1); k < M; ++k) GOI_SETSH(k, 0.f);
-#undef GOI_SETSH
-#undef GOI_SH
-        const float3 dL_ddir = make_float3(dx3[0] * dRGB[0] + dx3[1] * dRGB[1] + dx3[2] * dRGB[2],
-                                           dy3[0] * dRGB[0] + dy3[1] * dRGB[1] + dy3[2] * dRGB[2],
-                                           dz3[0] * dRGB[0] + dz3[1] * dRGB[1] + dz3[2] * dRGB[2]);
-        // dnormvdv, auxiliary.h:107-117
-        const float3 v = dir_orig;
-        const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
-        const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-        gmean.x += ((+sum2 - v.x * v.x) * dL_ddir.x - v.y * v.x * dL_ddir.y - v.z * v.x * dL_ddir.z) * invsum32;
-        gmean.y += (-v.x * v.y * dL_ddir.x + (sum2 - v.y * v.y) * dL_ddir.y - v.z * v.y * dL_ddir.z) * invsum32;
-        gmean.z += (-v.x * v.z * dL_ddir.x - v.y * v.z * dL_ddir.y + (sum2 - v.z * v.z) * dL_ddir.z) * invsum32;
-    }
-    dL_dmeans[3 * idx] = gmean.x; dL_dmeans[3 * idx + 1] = gmean.y; dL_dmeans[3 * idx + 2] = gmean.z;
-
     // ---- computeCov3D (backward), backward.cu:278-341 ----
     if (scales != nullptr) {
-        const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
-        const float r = q.x, x = q.y, y = q.z, z = q.w;
-        const M3 R = quat_R(q);
-        M3 S = m3_make(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
-        const float3 s = make_float3(scale_modifier * scales[3 * idx], scale_modifier * scales[3 * idx + 1],
-                                     scale_modifier * scales[3 * idx + 2]);
-        S.m[0][0] = s.x; S.m[1][1] = s.y; S.m[2][2] = s.z;
-        const M3 Mm = m3_mul(S, R);
-        const M3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2],
-                                     0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
-                                     0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
-        M3 M2;
+        float3 dsc = make_float3(0.f, 0.f, 0.f);
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            const M3 R = quat_R(q);
+            M3 S = m3_make(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
+            const float3 s = make_float3(scale_modifier * scales[3 * idx], scale_modifier * scales[3 * idx + 1],
+                                         scale_modifier * scales[3 * idx + 2]);
+            S.m[0][0] = s.x; S.m[1][1] = s.y; S.m[2][2] = s.z;
+            const M3 Mm = m3_mul(S, R);
+            const M3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2],
+                                         0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
+                                         0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
+            M3 M2;
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
+            for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
-            for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = Mm.m[cc][rr] * 2.0f;
-        const M3 dL_dM = m3_mul(M2, dL_dSigma);
-        const M3 Rt = m3_t(R);
-        M3 dMt = m3_t(dL_dM);
-        dL_dscale[3 * idx + 0] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-        dL_dscale[3 * idx + 1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-        dL_dscale[3 * idx + 2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+                for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = Mm.m[cc][rr] * 2.0f;
+            const M3 dL_dM = m3_mul(M2, dL_dSigma);
+            const M3 Rt = m3_t(R);
+            M3 dMt = m3_t(dL_dM);
+            dsc.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+            dsc.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+            dsc.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { dMt.m[0][k] *= s.x; dMt.m[1][k] *= s.y; dMt.m[2][k] *= s.z; }
-        float4 dq;
-        dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
-        dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
-        dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
-        dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+            for (int k = 0; k < 3; ++k) { dMt.m[0][k] *= s.x; dMt.m[1][k] *= s.y; dMt.m[2][k] *= s.z; }
+            dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+            dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+            dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+            dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        }
+        dL_dscale[3 * idx + 0] = dsc.x; dL_dscale[3 * idx + 1] = dsc.y; dL_dscale[3 * idx + 2] = dsc.z;
         *reinterpret_cast<float4*>(dL_drot + 4 * idx) = dq;
     }
 }
@@ -494,7 +595,7 @@ cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, con
     const float focal_y = v.height / (2.0f * v.tan_fovy);
     const float focal_x = v.width / (2.0f * v.tan_fovx);
     const float* cov3D_ptr = g.cov3D_precomp ? g.cov3D_precomp : gs.cov3D;    // rasterizer_impl.cu:579
-    k_preprocess_bwd<<<(P + 255) / 256, 256, 0, st>>>(
+    k_preprocess_bwd<<<(P + 127) / 128, 128, 0, st>>>(
         P, v.sh_degree, g.M, g.means3D, in.radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
         cov3D_ptr, v.viewmatrix, v.projmatrix, v.cam_pos, focal_x, focal_y, v.tan_fovx, v.tan_fovy,
         out.dL_dmean2D, out.dL_dconic, out.dL_dcolor, out.dL_ddepth,
