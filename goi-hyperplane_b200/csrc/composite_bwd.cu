@@ -248,6 +248,13 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const uint32_t list_idx = (uint32_t)(first_idx - j);
                 const float4 g0 = lds128(ag0 + j * 16);
                 const float4 g1 = lds128(ag1 + j * 16);
+                // payload row + Gaussian id: issued now so their latency hides behind the alpha evaluation
+                const uint32_t ap = apay + j * (ROW * 16);
+                const float4 p0 = lds128(ap);
+                float4 s4[NS4 > 0 ? NS4 : 1];
+#pragma unroll
+                for (int k = 0; k < NS4; ++k) s4[k] = lds128(ap + 16 + 16 * k);
+                const uint32_t id = (uint32_t)s_id[buf][j];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                 const float G = expf(power);
@@ -261,16 +268,13 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const float inv = rcp_approx(1.f - alpha);
                 const float Tn = T * inv;                   // reference: T = T / (1 - alpha)
                 const float wgt = alpha * Tn;
-                const uint32_t ap = apay + j * (ROW * 16);
-                const float4 p0 = lds128(ap);
                 float q = g_alpha;                          // q = payload . pixel-gradient + 1 * dL_dalpha
                 q = fmaf(p0.x, g_rgb[0], q); q = fmaf(p0.y, g_rgb[1], q); q = fmaf(p0.z, g_rgb[2], q);
                 q = fmaf(p0.w, g_depth, q);
 #pragma unroll
                 for (int k = 0; k < NS4; ++k) {
-                    const float4 s4 = lds128(ap + 16 + 16 * k);
-                    q = fmaf(s4.x, g_sem[4 * k + 0], q); q = fmaf(s4.y, g_sem[4 * k + 1], q);
-                    q = fmaf(s4.z, g_sem[4 * k + 2], q); q = fmaf(s4.w, g_sem[4 * k + 3], q);
+                    q = fmaf(s4[k].x, g_sem[4 * k + 0], q); q = fmaf(s4[k].y, g_sem[4 * k + 1], q);
+                    q = fmaf(s4[k].z, g_sem[4 * k + 2], q); q = fmaf(s4[k].w, g_sem[4 * k + 3], q);
                 }
                 const float accn = last_alpha * last_q + (1.f - last_alpha) * acc;
                 float dL_dopa = (q - accn) * Tn;
@@ -302,7 +306,6 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const float4 w4 = lds128(ar);
                 const float4 e0 = lds128(ar + grow0 * RSTRIDE * 4);
                 const float4 e1 = lds128(ar + grow1 * RSTRIDE * 4);
-                const uint32_t id = (uint32_t)s_id[buf][j];
 #pragma unroll
                 for (int k = 0; k < NBLK; ++k) {
                     float v[8];
