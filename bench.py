@@ -205,7 +205,7 @@ def run_ours(args):
     slots = [{k: torch.empty_like(v, device=dev) for k, v in host_w[0].items()} for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
-    loss_host = torch.zeros(2).pin_memory()
+    loss_host = [torch.zeros(2).pin_memory() for _ in range(2)]
 
     def prefetch(i):
         s = i % 2
@@ -226,7 +226,8 @@ def run_ours(args):
         freed[s].record()
         # D2H read of the step's result: the pseudo-loss value and the gradient norm of the semantic field
         loss = (out["semantics"].detach() * slots[s]["semantics"]).sum()
-        loss_host.copy_(torch.stack([loss, arena.slots['semantics'].norm()]), non_blocking=False)
+        # (asynchronous, like a trainer's logging: ordered on the stream, drained at the end of the region)
+        loss_host[i % 2].copy_(torch.stack([loss, arena.slots['semantics'].norm()]), non_blocking=True)
 
     for ev in freed:
         ev.record()

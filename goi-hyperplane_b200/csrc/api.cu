@@ -93,6 +93,12 @@ GeomState carve_geom(char* base, int P, int S)
     obtain(c, g.clamped, Pn);
     obtain(c, g.tiles_touched, Pn);
     obtain(c, g.point_offsets, Pn);
+    obtain(c, g.depth_keys[0], Pn);
+    obtain(c, g.depth_keys[1], Pn);
+    obtain(c, g.order[0], Pn);
+    obtain(c, g.order[1], Pn);
+    g.sortp_temp_bytes = sort_temp_bytes_for(P);
+    obtain(c, g.sortp_temp, g.sortp_temp_bytes);
     obtain(c, g.rect, Pn);
     g.scan_temp_bytes = scan_temp_bytes_for(P);
     obtain(c, g.scan_temp, g.scan_temp_bytes);
@@ -264,6 +270,19 @@ int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_f
     if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
     { StageScope sc(ST_COMPOSITE_FWD, st); GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], is, st), "composite forward"); }
     return debug_sync(view, st, "composite forward");
+}
+
+int goi_forward_auto(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, void* geom_buf,
+                     size_t geom_bytes, void* binning_buf, size_t binning_bytes, void* image_buf,
+                     size_t image_bytes, void* stream, int64_t* num_rendered)
+{
+    if (!out) return fail(GOI_ERR_INVALID_ARG, "out is NULL");
+    int rc = goi_forward_prepare(view, g, out->radii, geom_buf, geom_bytes, stream, num_rendered);
+    if (rc != GOI_OK) return rc;
+    if (binning_bytes < goi_binning_bytes(*num_rendered))
+        return fail(GOI_ERR_WORKSPACE, "binning buffer too small for %lld instances", (long long)*num_rendered);
+    return goi_forward_render(view, g, out, geom_buf, geom_bytes, binning_buf, binning_bytes, image_buf, image_bytes,
+                              *num_rendered, stream);
 }
 
 int goi_forward(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,

@@ -7,11 +7,17 @@
 //   cudaMemset(ranges) + identifyTileRanges                          (:314-321)
 //
 // Sort-order contract: ascending (tile, float bits of view-space depth), stable, pairs
-// emitted in ascending Gaussian index => equal keys resolve by ascending Gaussian index.  CUB's LSD
-// radix sort is stable, so the contract holds as long as emission order is by Gaussian index.
+// emitted in ascending Gaussian index => equal keys resolve by ascending Gaussian index.
 //
-// All of this is pure HBM streaming: 12 B written per instance by the emitter, a 64-bit-key /
-// 32-bit-value onesweep radix sort, 8 B read per instance for the range scan.
+// The reference sorts R instances on a 64-bit key in 6 radix passes (~152 B per instance).  The same
+// total order is produced here in two stable stages that move far fewer bytes:
+//   1. the P Gaussians are sorted ONCE by their 32-bit depth key (4 passes over 8 B records); ties keep
+//      ascending index because the input is in index order and the sort is stable;
+//   2. instances are emitted in that depth order (prefix sum over the depth-ordered tile counts), then
+//      stably sorted by tile id only: ceil(log2 tiles) <= 13..16 bits = 2 passes over 8 B records.
+// Stage 2 preserves the (depth, index) order inside each tile, so the result is identical to the
+// reference's single 64-bit sort.  Instances whose tile provably cannot reach alpha >= 1/255 are not
+// emitted at all (goi_cull.cuh).
 #include "goi_internal.cuh"
 #include "goi_cull.cuh"
 #include <cub/cub.cuh>
@@ -27,18 +33,40 @@ size_t scan_temp_bytes_for(int P)
 size_t sort_temp_bytes_for(int64_t R)
 {
     // Upper bound for cub::DeviceRadixSort (DoubleBuffer form: histograms + decoupled look-back
-    // descriptors only); checked at run time in run_binning().
+    // descriptors only); checked at run time.
     return (size_t)(R > 0 ? R : 0) / 4 + (1u << 20);
 }
 
+struct GatherTiles {
+    const uint32_t* tiles;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& idx) const { return tiles[idx]; }
+};
+
+// Stage 1 + prefix sum: depth-sort the Gaussians, then scan their instance counts in depth order.
 cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st)
 {
+    cub::DoubleBuffer<uint32_t> dk(gs.depth_keys[0], gs.depth_keys[1]);
+    cub::DoubleBuffer<uint32_t> dv(gs.order[0], gs.order[1]);
     size_t need = 0;
-    cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, need, gs.tiles_touched, gs.point_offsets, P, st);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, P, 0, 32, st);
+    if (e != cudaSuccess) return e;
+    if (need > gs.sortp_temp_bytes) return cudaErrorMemoryAllocation;
+    size_t bytes = gs.sortp_temp_bytes;
+    e = cub::DeviceRadixSort::SortPairs(gs.sortp_temp, bytes, dk, dv, P, 0, 32, st);
+    count_launches(2 + 4);
+    if (e != cudaSuccess) return e;
+    if (dv.selector != 0) {      // keep the rank -> index map in order[0] (4 passes: already there)
+        e = cudaMemcpyAsync(gs.order[0], gs.order[1], sizeof(uint32_t) * (size_t)P, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+
+    cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*> it(gs.order[0], GatherTiles{gs.tiles_touched});
+    need = 0;
+    e = cub::DeviceScan::InclusiveSum(nullptr, need, it, gs.point_offsets, P, st);
     if (e != cudaSuccess) return e;
     if (need > gs.scan_temp_bytes) return cudaErrorMemoryAllocation;
-    size_t bytes = gs.scan_temp_bytes;
-    e = cub::DeviceScan::InclusiveSum(gs.scan_temp, bytes, gs.tiles_touched, gs.point_offsets, P, st);
+    bytes = gs.scan_temp_bytes;
+    e = cub::DeviceScan::InclusiveSum(gs.scan_temp, bytes, it, gs.point_offsets, P, st);
     count_launches(2);                         // CUB: init + scan kernels
     if (e != cudaSuccess) return e;
     // R = point_offsets[P-1], kept on the device too (Meta::num_rendered)
@@ -46,47 +74,42 @@ cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st)
                            cudaMemcpyDeviceToDevice, st);
 }
 
-// One thread per Gaussian; emits its rect's tiles row-major, exactly the reference's loop nest.
-__global__ void __launch_bounds__(256) k_emit_keys(int P, const float4* __restrict__ geo,
-                                                   const float4* __restrict__ rgbd,
+// One thread per depth rank; emits that Gaussian's surviving tiles row-major (the reference's loop nest).
+__global__ void __launch_bounds__(256) k_emit_keys(int P, const uint32_t* __restrict__ order,
+                                                   const float4* __restrict__ geo,
                                                    const uint32_t* __restrict__ offsets,
-                                                   const uint2* __restrict__ rect, const int32_t* __restrict__ radii,
-                                                   int gx, int W, int H, uint64_t* __restrict__ keys,
-                                                   uint32_t* __restrict__ vals)
+                                                   const uint2* __restrict__ rect, int gx, int W, int H,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    if (!(radii[idx] > 0)) return;
-    uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
-    const uint32_t end = offsets[idx];
-    if (off == end) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    uint32_t off = (k == 0) ? 0 : offsets[k - 1];
+    const uint32_t end = offsets[k];
+    if (off == end) return;                   // culled, or no tile survives the exact test
+    const uint32_t idx = order[k];
     const uint2 rc = rect[idx];
     const uint32_t minx = rc.x & 0xffffu, miny = rc.x >> 16, maxx = rc.y & 0xffffu, maxy = rc.y >> 16;
-    const uint32_t depth_bits = __float_as_uint(rgbd[idx].w);
-    const float4 g0 = geo[2 * idx], g1 = geo[2 * idx + 1];
+    const float4 g0 = geo[2 * (size_t)idx], g1 = geo[2 * (size_t)idx + 1];
     for (uint32_t y = miny; y < maxy; ++y)
         for (uint32_t x = minx; x < maxx; ++x) {
             if (!tile_may_contribute(g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, (int)x, (int)y, W, H)) continue;
             if (off >= end) return;           // cannot happen (same bit-exact test as the count); never overrun
-            uint64_t key = (uint64_t)(y * (uint32_t)gx + x);
-            key <<= 32;
-            key |= depth_bits;
-            keys[off] = key;
-            vals[off] = (uint32_t)idx;
+            keys[off] = y * (uint32_t)gx + x;
+            vals[off] = idx;
             ++off;
         }
 }
 
-__global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint32_t* __restrict__ keys,
                                                      uint2* __restrict__ ranges)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L) return;
-    const uint32_t currtile = (uint32_t)(keys[idx] >> 32);
+    const uint32_t currtile = keys[idx];
     if (idx == 0)
         ranges[currtile].x = 0;
     else {
-        const uint32_t prevtile = (uint32_t)(keys[idx - 1] >> 32);
+        const uint32_t prevtile = keys[idx - 1];
         if (currtile != prevtile) {
             ranges[prevtile].y = (uint32_t)idx;
             ranges[currtile].x = (uint32_t)idx;
@@ -112,6 +135,7 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
                         const BinningState& bs, const ImageState& is, int64_t R, int* selector_out,
                         cudaStream_t st)
 {
+    (void)radii;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
     cudaError_t e;
     e = cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)gx * gy, st);
@@ -120,15 +144,15 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     if (R <= 0) return cudaSuccess;
 
     stage_begin(ST_EMIT, st);
-    k_emit_keys<<<(P + 255) / 256, 256, 0, st>>>(P, gs.geo, gs.rgbd, gs.point_offsets, gs.rect, radii, gx, v.width, v.height,
-                                                 bs.keys[0], bs.vals[0]);
+    k_emit_keys<<<(P + 255) / 256, 256, 0, st>>>(P, gs.order[0], gs.geo, gs.point_offsets, gs.rect, gx, v.width,
+                                                 v.height, bs.keys[0], bs.vals[0]);
     stage_end(ST_EMIT, st);
     count_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
-    const int end_bit = 32 + (int)higher_msb((uint32_t)(gx * gy));
-    cub::DoubleBuffer<uint64_t> dk(bs.keys[0], bs.keys[1]);
+    const int end_bit = (int)higher_msb((uint32_t)(gx * gy));
+    cub::DoubleBuffer<uint32_t> dk(bs.keys[0], bs.keys[1]);
     cub::DoubleBuffer<uint32_t> dv(bs.vals[0], bs.vals[1]);
     size_t need = 0;
     e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, R, 0, end_bit, st);
@@ -140,7 +164,6 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     stage_end(ST_SORT, st);
     count_launches(2 + (end_bit + 7) / 8);     // onesweep: histogram + scan + one kernel per 8-bit digit
     if (e != cudaSuccess) return e;
-    *selector_out = 0;
 
     stage_begin(ST_RANGES, st);
     k_tile_ranges<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, dk.Current(), is.ranges);
@@ -149,8 +172,7 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // The sorted Gaussian list always ends up in vals[0] so that the backward (which only has the
-    // opaque blob) needs no selector: with 41-45 key bits CUB runs an even number of passes and
-    // this copy is skipped.
+    // opaque blob) needs no selector.
     if (dv.selector != 0)
         e = cudaMemcpyAsync(bs.vals[0], bs.vals[1], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, st);
     return e;

@@ -61,7 +61,7 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp: x =
 }
 
 template <int NS4, int BATCH>
-__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 3 : 1))
 k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg, const float* __restrict__ out_alpha,
@@ -268,14 +268,14 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const float inv = rcp_approx(1.f - alpha);
                 const float Tn = T * inv;                   // reference: T = T / (1 - alpha)
                 const float wgt = alpha * Tn;
-                float q = g_alpha;                          // q = payload . pixel-gradient + 1 * dL_dalpha
-                q = fmaf(p0.x, g_rgb[0], q); q = fmaf(p0.y, g_rgb[1], q); q = fmaf(p0.z, g_rgb[2], q);
-                q = fmaf(p0.w, g_depth, q);
+                // q = payload . pixel-gradient + 1 * dL_dalpha, as four independent FMA chains (latency)
+                float q0 = fmaf(p0.x, g_rgb[0], g_alpha), q1 = p0.y * g_rgb[1], q2 = p0.z * g_rgb[2], q3 = p0.w * g_depth;
 #pragma unroll
                 for (int k = 0; k < NS4; ++k) {
-                    q = fmaf(s4[k].x, g_sem[4 * k + 0], q); q = fmaf(s4[k].y, g_sem[4 * k + 1], q);
-                    q = fmaf(s4[k].z, g_sem[4 * k + 2], q); q = fmaf(s4[k].w, g_sem[4 * k + 3], q);
+                    q0 = fmaf(s4[k].x, g_sem[4 * k + 0], q0); q1 = fmaf(s4[k].y, g_sem[4 * k + 1], q1);
+                    q2 = fmaf(s4[k].z, g_sem[4 * k + 2], q2); q3 = fmaf(s4[k].w, g_sem[4 * k + 3], q3);
                 }
+                const float q = (q0 + q1) + (q2 + q3);
                 const float accn = last_alpha * last_q + (1.f - last_alpha) * acc;
                 float dL_dopa = (q - accn) * Tn;
                 dL_dopa += (-T_final * inv) * bg_dot_dpixel;

@@ -30,8 +30,12 @@ struct GeomState {
     float4*   rgbd;
     float*    cov3D;             // [P,6]
     uint8_t*  clamped;           // [P] bit c set = colour channel c was clamped at 0
-    uint32_t* tiles_touched;     // [P]
-    uint32_t* point_offsets;     // [P] inclusive prefix sum
+    uint32_t* tiles_touched;     // [P]   instances of Gaussian i (after exact tile culling)
+    uint32_t* point_offsets;     // [P]   inclusive prefix sum of tiles_touched IN DEPTH ORDER
+    uint32_t* depth_keys[2];     // [P]x2 float bits of the view depth (0xffffffff = culled), double buffer
+    uint32_t* order[2];          // [P]x2 Gaussian indices; after the depth sort: back-to-front rank -> index
+    char*     sortp_temp;        // CUB temp of the per-Gaussian depth sort
+    size_t    sortp_temp_bytes;
     uint2*    rect;              // [P]
     Meta*     meta;
     char*     scan_temp;
@@ -44,7 +48,7 @@ struct ImageState {
     size_t    total_bytes;
 };
 struct BinningState {
-    uint64_t* keys[2];           // double buffer: tile<<32 | depth bits
+    uint32_t* keys[2];           // double buffer: tile id (instances are emitted in depth order)
     uint32_t* vals[2];           // double buffer: Gaussian index
     uint32_t* selector;          // (device) unused; host keeps the selector in the header word below
     char*     sort_temp;

@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
     const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int gx, int gy, int prefiltered,
     int32_t* __restrict__ radii, float4* __restrict__ geo, float4* __restrict__ rgbd, float* __restrict__ cov3Ds,
-    uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rect, Meta* meta)
+    uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rect,
+    uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ order, Meta* meta)
 {
     // One warp = 32 consecutive Gaussians.  The per-Gaussian geometry is computed first; the SH rows of the
     // whole warp (32 x 3M contiguous floats) are then staged through shared memory with coalesced loads,
@@ -182,6 +183,8 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
         if (idx >= P) break;
         radii[idx] = 0;
         tiles_touched[idx] = 0;
+        depth_keys[idx] = 0xffffffffu;                  // culled Gaussians sort behind everything
+        order[idx] = (uint32_t)idx;
 
         // in_frustum, auxiliary.h:139-164
         p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
         for (int tx = minx; tx < maxx; ++tx)
             touched += tile_may_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, power_cut, tx, ty, W, H) ? 1u : 0u;
     tiles_touched[idx] = touched;
+    if (touched) depth_keys[idx] = __float_as_uint(depth);
 }
 
 cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int32_t* radii, const GeomState& gs,
@@ -322,7 +326,7 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
         P, v.sh_degree, g.M, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
         g.cov3D_precomp, g.colors_precomp, v.viewmatrix, v.projmatrix, v.cam_pos, v.width, v.height,
         v.tan_fovx, v.tan_fovy, focal_x, focal_y, gx, gy, v.prefiltered, radii, gs.geo, gs.rgbd, gs.cov3D,
-        gs.clamped, gs.tiles_touched, gs.rect, gs.meta);
+        gs.clamped, gs.tiles_touched, gs.rect, gs.depth_keys[0], gs.order[0], gs.meta);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -88,6 +88,9 @@ SYMBOLS = {
     "goi_forward_render": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                      C.c_int64, C.c_void_p]),
+    "goi_forward_auto": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                   C.c_void_p, C.POINTER(C.c_int64)]),
     "goi_forward": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
                               ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p,
                               C.POINTER(C.c_int64)]),
@@ -126,6 +129,7 @@ def _grad_out(name, shape, f32):
         return t.view(shape)
     return torch.empty(shape, **f32)
 
+_r_guess = 0               # running upper estimate of the instance count (sizes the binning blob)
 last_num_rendered = 0      # R of the most recent forward on this thread (bench.py's roofline arithmetic)
 
 _lib = None
@@ -232,14 +236,22 @@ def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotatio
         img = torch.empty((img_bytes,), **u8)
         stream = _stream(dev)
         R = C.c_int64(0)
-        _check(L.goi_forward_prepare(C.byref(view), C.byref(g), _ptr(radii), geom.data_ptr(), geom_bytes, stream,
-                                     C.byref(R)), "goi_forward_prepare")
-        bin_bytes = L.goi_binning_bytes(R.value)
-        binning = torch.empty((bin_bytes,), **u8)
         out = goi_fwd_out(_ptr(out_color), _ptr(out_sem), _ptr(out_depth), _ptr(out_alpha), _ptr(radii))
-        _check(L.goi_forward_render(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
-                                    binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, R.value, stream),
-               "goi_forward_render")
+        # The binning blob is sized BEFORE the instance count is known (a guess from recent views, with
+        # headroom), so prepare + render run inside one C call and the device is refilled right after the
+        # one host sync of the path; a wrong guess costs one re-allocation.
+        global _r_guess
+        bin_bytes = L.goi_binning_bytes(max(int(_r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
+        binning = torch.empty((bin_bytes,), **u8)
+        rc = L.goi_forward_auto(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
+                                binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, stream, C.byref(R))
+        if rc == -3 and R.value > 0 and L.goi_binning_bytes(R.value) > bin_bytes:
+            bin_bytes = L.goi_binning_bytes(R.value)
+            binning = torch.empty((bin_bytes,), **u8)
+            rc = L.goi_forward_render(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
+                                      binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, R.value, stream)
+        _check(rc, "goi_forward")
+        _r_guess = max(R.value, int(0.9 * _r_guess))
     global last_num_rendered
     last_num_rendered = int(R.value)
     return int(R.value), out_color, out_sem, out_depth, out_alpha, radii, geom, binning, img

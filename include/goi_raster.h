@@ -163,6 +163,15 @@ int goi_forward_render(const goi_view* view, const goi_gaussians* g,
                        void* image_buf, size_t image_bytes,
                        int64_t num_rendered, void* stream);
 
+/* ---- forward, single call with caller-sized blobs: prepare + (if binning_bytes suffices) render without
+ * returning to the host language in between, so the device is refilled microseconds after the
+ * num_rendered read-back.  *num_rendered is always set; if the binning blob is too small the call
+ * returns GOI_ERR_WORKSPACE having done only the prepare phase: re-allocate with
+ * goi_binning_bytes(*num_rendered) and call goi_forward_render. */
+int goi_forward_auto(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
+                     void* geom_buf, size_t geom_bytes, void* binning_buf, size_t binning_bytes,
+                     void* image_buf, size_t image_bytes, void* stream, int64_t* num_rendered);
+
 /* ---- forward, callback form: signature-for-signature stand-in for
  * Rasterizer::forward (rasterizer.h:34-62).  Returns num_rendered through
  * *num_rendered (the reference returns it as the int result). */

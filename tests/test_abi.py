@@ -58,7 +58,7 @@ def test_scratch_sizes_are_monotone_and_host_only():
     assert L.goi_geom_bytes(0, 0) > 0
     a, b = L.goi_geom_bytes(1000, 16), L.goi_geom_bytes(1_000_000, 16)
     assert 0 < a < b and b > 1_000_000 * 80
-    assert L.goi_binning_bytes(0) > 0 and L.goi_binning_bytes(4_000_000) >= 4_000_000 * 24
+    assert L.goi_binning_bytes(0) > 0 and L.goi_binning_bytes(4_000_000) >= 4_000_000 * 16
     assert L.goi_image_bytes(1600, 1000) >= 1600 * 1000 * 4 + 6300 * 8
 
 
