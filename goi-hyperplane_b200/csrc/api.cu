@@ -40,13 +40,17 @@ static int debug_sync(const goi_view* v, cudaStream_t st, const char* where)
 }
 
 // ---- measurement hooks --------------------------------------------------------------------------
-struct Timing {
-    bool enabled = false, created = false;
-    cudaEvent_t ev[ST_COUNT][2];
-    bool valid[ST_COUNT] = {};
-};
 // Process-wide (not thread-local): PyTorch runs autograd's backward on its own worker thread, and the
 // forward and backward of one view must land in the same record.  Measurement only; guarded by a mutex.
+// Events are kept in a ring of TIMING_SLOTS views so that reading them needs no per-view host sync:
+// a new slot starts at every preprocess stage (= every forward).
+constexpr int TIMING_SLOTS = 64;
+struct Timing {
+    bool enabled = false, created = false;
+    cudaEvent_t ev[TIMING_SLOTS][ST_COUNT][2];
+    bool valid[TIMING_SLOTS][ST_COUNT] = {};
+    long long views = 0;            // forwards recorded since enable
+};
 static Timing g_timing;
 static std::mutex g_timing_mu;
 static std::atomic<uint64_t> g_launches{0};
@@ -58,18 +62,26 @@ void stage_begin(Stage s, cudaStream_t st)
     if (!t.enabled) return;
     std::lock_guard<std::mutex> lk(g_timing_mu);
     if (!t.created) {
-        for (int i = 0; i < ST_COUNT; ++i) { cudaEventCreate(&t.ev[i][0]); cudaEventCreate(&t.ev[i][1]); }
+        for (int k = 0; k < TIMING_SLOTS; ++k)
+            for (int i = 0; i < ST_COUNT; ++i) { cudaEventCreate(&t.ev[k][i][0]); cudaEventCreate(&t.ev[k][i][1]); }
         t.created = true;
     }
-    cudaEventRecord(t.ev[s][0], st);
+    if (s == ST_PREPROCESS) {
+        ++t.views;
+        const int slot = (int)((t.views - 1) % TIMING_SLOTS);
+        for (int i = 0; i < ST_COUNT; ++i) t.valid[slot][i] = false;
+    }
+    if (t.views == 0) return;
+    cudaEventRecord(t.ev[(t.views - 1) % TIMING_SLOTS][s][0], st);
 }
 void stage_end(Stage s, cudaStream_t st)
 {
     Timing& t = g_timing;
-    if (!t.enabled || !t.created) return;
+    if (!t.enabled || !t.created || t.views == 0) return;
     std::lock_guard<std::mutex> lk(g_timing_mu);
-    cudaEventRecord(t.ev[s][1], st);
-    t.valid[s] = true;
+    const int slot = (int)((t.views - 1) % TIMING_SLOTS);
+    cudaEventRecord(t.ev[slot][s][1], st);
+    t.valid[slot][s] = true;
 }
 
 template <typename T>
@@ -181,7 +193,9 @@ int goi_timing_enable(int on)
 {
     std::lock_guard<std::mutex> lk(g_timing_mu);
     g_timing.enabled = on != 0;
-    for (int i = 0; i < ST_COUNT; ++i) g_timing.valid[i] = false;
+    g_timing.views = 0;
+    for (int k = 0; k < TIMING_SLOTS; ++k)
+        for (int i = 0; i < ST_COUNT; ++i) g_timing.valid[k][i] = false;
     return GOI_OK;
 }
 int goi_timing_read(float* ms)
@@ -189,13 +203,19 @@ int goi_timing_read(float* ms)
     if (!ms) return fail(GOI_ERR_INVALID_ARG, "null ms");
     std::lock_guard<std::mutex> lk(g_timing_mu);
     for (int i = 0; i < ST_COUNT; ++i) {
-        ms[i] = -1.f;
-        if (g_timing.created && g_timing.valid[i]) {
-            cudaError_t e = cudaEventSynchronize(g_timing.ev[i][1]);
+        double sum = 0.0;
+        int n = 0;
+        for (int k = 0; k < TIMING_SLOTS && g_timing.created; ++k) {
+            if (!g_timing.valid[k][i]) continue;
+            cudaError_t e = cudaEventSynchronize(g_timing.ev[k][i][1]);
             if (e != cudaSuccess) return cuda_fail(e, "timing sync");
-            e = cudaEventElapsedTime(&ms[i], g_timing.ev[i][0], g_timing.ev[i][1]);
+            float t = 0.f;
+            e = cudaEventElapsedTime(&t, g_timing.ev[k][i][0], g_timing.ev[k][i][1]);
             if (e != cudaSuccess) return cuda_fail(e, "timing read");
+            sum += t;
+            ++n;
         }
+        ms[i] = n ? (float)(sum / n) : -1.f;
     }
     return GOI_OK;
 }

@@ -396,7 +396,7 @@ def timing_enable(on: bool) -> None:
 
 
 def timing_read() -> dict:
-    """ms of the most recent occurrence of every pipeline stage (synchronises on their events)."""
+    """Mean ms per view of every pipeline stage over the (up to 64) views recorded since timing_enable(True)."""
     buf = (C.c_float * GOI_NUM_STAGES)()
     _check(lib().goi_timing_read(buf), "goi_timing_read")
     return {lib().goi_stage_name(i).decode(): float(buf[i]) for i in range(GOI_NUM_STAGES)}

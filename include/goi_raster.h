@@ -263,8 +263,9 @@ int goi_read_stats(const goi_view* view, const goi_gaussians* g,
 
 /* ---- per-stage device timing + launch accounting (measurement hooks for bench.py).
  * When enabled (process-wide), every pipeline stage is bracketed by CUDA events on the
- * caller's stream; goi_timing_read synchronises on them and returns the duration in ms of the
- * most recent occurrence of each stage (-1 if it did not run).  Stage order:
+ * caller's stream, kept in a ring of the last 64 views; goi_timing_read synchronises on them and
+ * returns, per stage, the MEAN duration in ms over the views recorded since goi_timing_enable(1)
+ * (-1 if the stage did not run), so no per-view host sync is needed.  Stage order:
  *   0 preprocess  1 prefix-sum  2 key-emit  3 radix-sort  4 tile-ranges  5 composite-forward
  *   6 zero-grads  7 composite-backward  8 preprocess-backward
  * goi_launch_count returns how many kernels (own kernels + CUB's) the library has launched. */
