@@ -146,14 +146,24 @@ def run_ours(args):
 
     outs = ("render", "semantics", "depth", "alpha")
 
-    def step(i, weights):
-        """One training-view pass: render() forward, then backward from dL/d(outputs) = the weights of the
-        linear pseudo-loss L = sum(w * out) (its exact gradient), down to every per-Gaussian parameter."""
-        cam = cams[(i * world + rank) % N_VIEWS]
-        arena.clear_grads()
-        out = render(cam, g, pipe, bg)
-        with arena:
-            torch.autograd.backward([out[k] for k in outs], [weights[k] for k in outs])
+    vps = args.views_per_step
+
+    def step(i, weights, after_view=None):
+        """One data-parallel step: `vps` training views per rank, each a render() forward + backward from
+        dL/d(outputs) = the weights of the linear pseudo-loss L = sum(w * out) (its exact gradient) down to
+        every per-Gaussian parameter; views after the first ADD their gradients in place to the flat buffer
+        (goi_bwd_out.accumulate); one NCCL all-reduce of that buffer ends the step (BASELINE config 4 shards
+        64 views over 8 GPUs the same way: 8 views per rank per all-reduce)."""
+        for v in range(vps):
+            view = i * vps + v                       # this rank's running view counter
+            cam = cams[(view * world + rank) % N_VIEWS]
+            wv = weights(view) if callable(weights) else weights
+            arena.clear_grads()
+            out = render(cam, g, pipe, bg)
+            with arena.accumulating(v > 0):
+                torch.autograd.backward([out[k] for k in outs], [wv[k] for k in outs])
+            if after_view is not None:
+                after_view(view, out, wv)
         if world > 1:
             arena.all_reduce()
         return out
@@ -188,16 +198,16 @@ def run_ours(args):
 
     def resident_step(i):
         step(i, w_dev)
-        rs.append(_C.last_num_rendered)
+        rs.append(_C.last_num_rendered)       # (of the step's last view; the poses differ by a few degrees)
 
     ms_total = timed(resident_step, args.steps)
     # per-stage CUDA-event times of the timed region's views (ring of the last 64), read after the region
     for k, v in _C.timing_read().items():
-        stage_acc[k] = max(v, 0.0) * args.steps
+        stage_acc[k] = max(v, 0.0) * args.steps          # mean ms per VIEW x steps
     launches = _C.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else {}
     _C.timing_enable(False)
-    value = world * args.steps / (ms_total / 1e3)
+    value = world * vps * args.steps / (ms_total / 1e3)
 
     # ---------------- end-to-end arm: per-view inputs from pinned host memory ----------------
     host_w = [{k: v.cpu().pin_memory() for k, v in make_loss_weights(S, W, H, seed + j).items()} for j in range(2)]
@@ -208,36 +218,47 @@ def run_ours(args):
     freed = [torch.cuda.Event(), torch.cuda.Event()]
     loss_host = [torch.zeros(2).pin_memory() for _ in range(2)]
 
-    def prefetch(i):
-        s = i % 2
+    n_e2e_views = args.steps * vps
+
+    def prefetch(view):
+        s = view % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[s])
             for k in slots[s]:
-                slots[s][k].copy_(host_w[i % 2][k], non_blocking=True)
+                slots[s][k].copy_(host_w[view % 2][k], non_blocking=True)
             ready[s].record(copy_stream)
 
-    def e2e_step(i):
-        if i == 0:
-            prefetch(0)
-        if i + 1 < args.steps:
-            prefetch(i + 1)                          # overlaps this step's compute
-        s = i % 2
-        torch.cuda.current_stream().wait_event(ready[s])
-        out = step(i, slots[s])
-        freed[s].record()
-        # D2H read of the step's result: the pseudo-loss value and the gradient norm of the semantic field
-        loss = (out["semantics"].detach() * slots[s]["semantics"]).sum()
+    def view_inputs(view):
+        """Called right before a view's forward: start the NEXT view's host->device copy (it overlaps this
+        view's compute), then make the compute stream wait for this view's own copy."""
+        if view % n_e2e_views == 0:
+            prefetch(view)
+        if (view + 1) % n_e2e_views != 0:
+            prefetch(view + 1)
+        torch.cuda.current_stream().wait_event(ready[view % 2])
+        return slots[view % 2]
+
+    def view_done(view, out, wv):
+        # D2H read of the view's result: the pseudo-loss value and the gradient norm of the semantic field
         # (asynchronous, like a trainer's logging: ordered on the stream, drained at the end of the region)
-        loss_host[i % 2].copy_(torch.stack([loss, arena.slots['semantics'].norm()]), non_blocking=True)
+        loss = (out["semantics"].detach() * wv["semantics"]).sum()
+        loss_host[view % 2].copy_(torch.stack([loss, arena.slots['semantics'].norm()]), non_blocking=True)
+        freed[view % 2].record()                  # the slot may now be overwritten by the copy stream
+
+    def e2e_step(i):
+        step(i, view_inputs, view_done)
 
     for ev in freed:
         ev.record()
+    n_e2e_views = min(2, args.warmup) * vps
     for i in range(min(2, args.warmup)):
         e2e_step(i)
+    torch.cuda.synchronize()
     for ev in freed:
         ev.record()
+    n_e2e_views = args.steps * vps
     ms_e2e = timed(e2e_step, args.steps)
-    e2e_value = world * args.steps / (ms_e2e / 1e3)
+    e2e_value = world * vps * args.steps / (ms_e2e / 1e3)
 
     if rank != 0:
         return
@@ -253,12 +274,14 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
                                f"fwd+bwd of all four outputs, {N_VIEWS} camera poses",
-                   "views_per_step": world, "parallelism": f"view-dp{world}",
+                   "views_per_step": world * vps, "views_per_gpu_per_step": vps,
+                   "parallelism": f"view-dp{world}, one all-reduce of the flat f32 gradient buffer per step",
                    "l2_policy": "inputs larger than L2 (300 MB parameters + 98 MB sort buffers per view)",
                    "num_rendered_mean": round(R)},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "ms_per_view": round(ms_total / args.steps / vps, 4),
+        "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes * vps,
+                "d2h_bytes_per_step": 8 * vps, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
@@ -354,6 +377,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--views-per-step", type=int, default=4,
+                    help="training views per GPU per step (gradients summed in place, one all-reduce per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -31,11 +31,11 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src: str, force: bool, verbose: bool) -> str:
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+def _compile(src: str, force: bool, verbose: bool, stats: bool = False) -> str:
+    obj = os.path.join(OBJ, src.replace(".cu", ".stats.o" if stats else ".o"))
     path = os.path.join(CSRC, src)
     if force or _stale(obj, [path] + HEADERS):
-        cmd = [NVCC, *FLAGS, "-c", path, "-o", obj]
+        cmd = [NVCC, *FLAGS, *(["-DGOI_STATS"] if stats else []), "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -46,17 +46,20 @@ def _compile(src: str, force: bool, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, stats: bool = False) -> str:
+    """stats=True builds the instrumented twin lib/libgoi_raster_stats.so (work counters in the composite
+    kernels, -DGOI_STATS) used by profiles/work_counters.py; the product library never carries them."""
     os.makedirs(OBJ, exist_ok=True)
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    lib = LIB.replace(".so", "_stats.so") if stats else LIB
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
-    if force or _stale(LIB, objs):
+        objs = list(ex.map(lambda s: _compile(s, force, verbose, stats), SOURCES))
+    if force or _stale(lib, objs):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-Xcompiler", "-fPIC", *objs, "-o", LIB]
+               "-Xcompiler", "-fPIC", *objs, "-o", lib]
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, stats="--stats" in sys.argv))

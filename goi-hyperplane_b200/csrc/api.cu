@@ -349,13 +349,16 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
     BinningState bs = carve_binning((char*)binning_buf, num_rendered);
 
     // accumulators of the composite backward (everything else is fully written by k_preprocess_bwd)
+    // (in accumulate mode the arrays that ARE input gradients keep their contents: the atomics add to them)
+    const bool acc = out->accumulate != 0;
     stage_begin(ST_ZERO, st);
     GOI_CUDA(cudaMemsetAsync(out->dL_dmean2D, 0, sizeof(float) * 3 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_dconic, 0, sizeof(float) * 4 * P, st), "zero grads");
-    GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
-    GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
+    if (!acc) GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
+    if (!acc || g->colors_precomp == nullptr)
+        GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_ddepth, 0, sizeof(float) * P, st), "zero grads");
-    if (g->S > 0) GOI_CUDA(cudaMemsetAsync(out->dL_dsemantic, 0, sizeof(float) * (size_t)g->S * P, st), "zero grads");
+    if (g->S > 0 && !acc) GOI_CUDA(cudaMemsetAsync(out->dL_dsemantic, 0, sizeof(float) * (size_t)g->S * P, st), "zero grads");
     stage_end(ST_ZERO, st);
 
     if (num_rendered > 0) {

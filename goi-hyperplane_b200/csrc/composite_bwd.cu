@@ -222,6 +222,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
     const uint32_t a_dyn = smem_u32(s_red + warp * (2 * DROWS * RSTRIDE));
     uint32_t flip = 0;                                 // byte offset of the current half of the double buffer
+    GOI_STAT_DECL;
 
     if (nb > 0) stage(0);
     for (int b = 0; b < nb; ++b) {
@@ -242,9 +243,11 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 keep = rect_may_contribute(a.x, a.y, a.z, a.w, q.x, q.z, rx0, rx1, ry0, ry1);
             }
             unsigned m = __ballot_sync(0xffffffffu, keep);
+            GOI_STAT_ADD(0, (c0 + lane < cnt) ? 1u : 0u);
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
                 m &= m - 1;
+                GOI_STAT_ADD(1, lane == 0 ? 1u : 0u);
                 const uint32_t list_idx = (uint32_t)(first_idx - j);
                 const float4 g0 = lds128(ag0 + j * 16);
                 const float4 g1 = lds128(ag1 + j * 16);
@@ -263,6 +266,8 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const bool hit = (list_idx < last_contributor) && !(power > 0.0f) && !(power < g1.z) &&
                                  !(alpha < 1.0f / 255.0f);
                 if (!__any_sync(0xffffffffu, hit)) continue;
+                GOI_STAT_ADD(2, lane == 0 ? 1u : 0u);
+                GOI_STAT_ADD(3, hit ? 1u : 0u);
 
                 // ---- per-pixel values (branch-free; rejected lanes publish zeros) ----
                 const float inv = rcp_approx(1.f - alpha);
@@ -325,6 +330,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
             }
         }
     }
+    GOI_STAT_FLUSH(4);
 }
 
 template <int NS4>
@@ -364,3 +370,16 @@ cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, cons
 }
 
 }  // namespace goi
+
+#ifdef GOI_STATS
+// instrumented build only: read (and optionally reset) this translation unit's work counters
+extern "C" int goi_debug_work_bwd(unsigned long long* out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, goi::g_work, sizeof(goi::g_work));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0};
+        e = cudaMemcpyToSymbol(goi::g_work, z, sizeof(z));
+    }
+    return e == cudaSuccess ? 0 : -2;
+}
+#endif

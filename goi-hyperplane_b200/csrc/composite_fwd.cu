@@ -105,6 +105,7 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     int done = inside ? 0 : 1;                          // int, not bool: keeps the loop free of byte packing
     bool warp_done = __all_sync(0xffffffffu, done);
     const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
+    GOI_STAT_DECL;
 
     if (nb > 0) stage(0);
     for (int b = 0; b < nb; ++b) {
@@ -127,9 +128,11 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 keep = rect_may_contribute(a.x, a.y, a.z, a.w, q.x, q.z, rx0, rx1, ry0, ry1);
             }
             unsigned m = __ballot_sync(0xffffffffu, keep);
+            GOI_STAT_ADD(0, (c0 + lane < cnt) ? 1u : 0u);
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
                 m &= m - 1;
+                GOI_STAT_ADD(1, lane == 0 ? 1u : 0u);
                 const float4 g0 = lds128(ag0 + j * 16);
                 const float4 g1 = lds128(ag1 + j * 16);
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
@@ -142,6 +145,8 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const bool hit = valid && !fin;
                 done |= fin ? 1 : 0;
                 if (__any_sync(0xffffffffu, hit)) {
+                    GOI_STAT_ADD(2, lane == 0 ? 1u : 0u);
+                    GOI_STAT_ADD(3, hit ? 1u : 0u);
                     const float w = hit ? alpha * T : 0.f;
                     const uint32_t ap = apay + j * (ROW * 16);
                     const float4 p0 = lds128(ap);
@@ -170,6 +175,7 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         }
     }
 
+    GOI_STAT_FLUSH(0);
     if (inside) {
         n_contrib[pix] = last_contributor;
         out_color[pix] = C0 + T * bg[0];
@@ -234,3 +240,16 @@ cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float*
 }
 
 }  // namespace goi
+
+#ifdef GOI_STATS
+// instrumented build only: read (and optionally reset) this translation unit's work counters
+extern "C" int goi_debug_work_fwd(unsigned long long* out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, goi::g_work, sizeof(goi::g_work));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0};
+        e = cudaMemcpyToSymbol(goi::g_work, z, sizeof(z));
+    }
+    return e == cudaSuccess ? 0 : -2;
+}
+#endif

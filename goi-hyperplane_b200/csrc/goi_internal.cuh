@@ -110,6 +110,22 @@ cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st);
 
 // ---- small device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__
+// Work counters of the composite kernels, compiled only into the instrumented build
+// (build.py --stats -> lib/libgoi_raster_stats.so); never part of the product library.
+//   [0] (warp, instance) cull tests   [1] warp walks (cull survivors)   [2] walks with >= 1 blending lane
+//   [3] blending (pixel, instance) pairs   -- forward in [0..3], backward in [4..7]
+#ifdef GOI_STATS
+static __device__ unsigned long long g_work[8];   // one copy per translation unit
+#define GOI_STAT_DECL unsigned int st_[4] = {0u, 0u, 0u, 0u}
+#define GOI_STAT_ADD(i, n) st_[i] += (n)
+#define GOI_STAT_FLUSH(base) do { for (int i_ = 0; i_ < 4; ++i_) { unsigned int v_ = st_[i_]; \
+    for (int o_ = 16; o_ >= 1; o_ >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, o_); \
+    if ((threadIdx.x & 31) == 0 && v_) atomicAdd(&g_work[(base) + i_], (unsigned long long)v_); } } while (0)
+#else
+#define GOI_STAT_DECL
+#define GOI_STAT_ADD(i, n)
+#define GOI_STAT_FLUSH(base)
+#endif
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

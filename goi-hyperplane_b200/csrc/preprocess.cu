@@ -135,21 +135,34 @@ __device__ __forceinline__ void sh_tile_load(float* tile, const float* __restric
         }
     }
 }
-__device__ __forceinline__ void sh_tile_store(float* __restrict__ dst, const float* tile, int rows, int rowlen, int lane)
+// acc: add to what dst already holds (gradient accumulation over views) instead of overwriting it.
+__device__ __forceinline__ void sh_tile_store(float* __restrict__ dst, const float* tile, int rows, int rowlen, int lane,
+                                              bool acc)
 {
     if (rowlen == 48 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
         float4* dst4 = reinterpret_cast<float4*>(dst);
+        float4 old[12];
+        if (acc) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int f = lane + 32 * k;
+                old[k] = (f < rows * 12) ? dst4[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const int f = lane + 32 * k;
             const float* d = tile + (f / 12) * PRE_ROWSTRIDE + (f % 12) * 4;
-            if (f < rows * 12) dst4[f] = make_float4(d[0], d[1], d[2], d[3]);
+            float4 v = make_float4(d[0], d[1], d[2], d[3]);
+            if (acc) { v.x += old[k].x; v.y += old[k].y; v.z += old[k].z; v.w += old[k].w; }
+            if (f < rows * 12) dst4[f] = v;
         }
     } else {
         int r = 0, col = lane;
         while (col >= rowlen) { col -= rowlen; ++r; }
         for (int i = lane; i < rows * rowlen; i += 32) {
-            dst[i] = tile[r * PRE_ROWSTRIDE + col];
+            const float v = tile[r * PRE_ROWSTRIDE + col];
+            dst[i] = acc ? dst[i] + v : v;
             col += 32;
             while (col >= rowlen) { col -= rowlen; ++r; }
         }
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
     const float* __restrict__ dL_dmean2D, const float* __restrict__ dL_dconics, const float* __restrict__ dL_dcolor,
     const float* __restrict__ dL_ddepth,
     float* __restrict__ dL_dmeans, float* __restrict__ dL_dcov, float* __restrict__ dL_dsh,
-    float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
+    float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int acc, int acc_cov)
 {
     // One warp = 32 consecutive Gaussians; their SH rows (and the dL_dsh rows) are 32 x 3M contiguous floats
     // and move through one shared-memory tile with fully coalesced global accesses.
@@ -544,13 +557,20 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
                 row[3 * k + 2] = coef[k] * dRGB[2];
             }
         __syncwarp();
-        sh_tile_store(dL_dsh + (size_t)base * rowlen, tile, rows, rowlen, lane);
+        // (accumulate mode: a warp whose Gaussians are all culled adds nothing -- skip the read-modify-write)
+        if (!acc || __any_sync(0xffffffffu, active))
+            sh_tile_store(dL_dsh + (size_t)base * rowlen, tile, rows, rowlen, lane, acc != 0);
     }
     if (!in_range) return;
-    dL_dmeans[3 * idx] = gmean.x; dL_dmeans[3 * idx + 1] = gmean.y; dL_dmeans[3 * idx + 2] = gmean.z;
+    if (acc) {
+        if (!active) return;                  // zero contribution
+        dL_dmeans[3 * idx] += gmean.x; dL_dmeans[3 * idx + 1] += gmean.y; dL_dmeans[3 * idx + 2] += gmean.z;
+    } else {
+        dL_dmeans[3 * idx] = gmean.x; dL_dmeans[3 * idx + 1] = gmean.y; dL_dmeans[3 * idx + 2] = gmean.z;
+    }
     if (dL_dcov) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) dL_dcov[6 * idx + i] = dcov[i];
+        for (int i = 0; i < 6; ++i) dL_dcov[6 * idx + i] = acc_cov ? dL_dcov[6 * idx + i] + dcov[i] : dcov[i];
     }
 
     // ---- computeCov3D (backward), backward.cu:278-341 ----
@@ -587,6 +607,11 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
             dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
             dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
         }
+        if (acc) {
+            dsc.x += dL_dscale[3 * idx + 0]; dsc.y += dL_dscale[3 * idx + 1]; dsc.z += dL_dscale[3 * idx + 2];
+            const float4 o = *reinterpret_cast<const float4*>(dL_drot + 4 * idx);
+            dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+        }
         dL_dscale[3 * idx + 0] = dsc.x; dL_dscale[3 * idx + 1] = dsc.y; dL_dscale[3 * idx + 2] = dsc.z;
         *reinterpret_cast<float4*>(dL_drot + 4 * idx) = dq;
     }
@@ -604,7 +629,8 @@ cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, con
         cov3D_ptr, v.viewmatrix, v.projmatrix, v.cam_pos, focal_x, focal_y, v.tan_fovx, v.tan_fovy,
         out.dL_dmean2D, out.dL_dconic, out.dL_dcolor, out.dL_ddepth,
         out.dL_dmean3D, out.dL_dcov3D, g.shs ? out.dL_dsh : nullptr,
-        g.scales ? out.dL_dscale : nullptr, g.scales ? out.dL_drot : nullptr);
+        g.scales ? out.dL_dscale : nullptr, g.scales ? out.dL_drot : nullptr, out.accumulate != 0,
+        out.accumulate != 0 && g.cov3D_precomp != nullptr);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -25,7 +25,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GOI_RASTER_LIB", os.path.join(_HERE, "..", "lib", "libgoi_raster.so"))
-GOI_ABI_VERSION = 1
+GOI_ABI_VERSION = 2
 GOI_MAX_SEM = 64
 GOI_MASK_APE, GOI_MASK_OSH = 0, 1
 
@@ -58,7 +58,8 @@ class goi_bwd_in(C.Structure):
 class goi_bwd_out(C.Structure):
     _fields_ = [("dL_dmean2D", _f32p), ("dL_dconic", _f32p), ("dL_dopacity", _f32p), ("dL_dcolor", _f32p),
                 ("dL_dsemantic", _f32p), ("dL_ddepth", _f32p), ("dL_dmean3D", _f32p), ("dL_dcov3D", _f32p),
-                ("dL_dsh", _f32p), ("dL_dscale", _f32p), ("dL_drot", _f32p)]
+                ("dL_dsh", _f32p), ("dL_dscale", _f32p), ("dL_drot", _f32p), ("accumulate", C.c_int32),
+                ("_pad", C.c_int32)]
 
 
 class goi_mask_args(C.Structure):
@@ -113,12 +114,16 @@ GOI_NUM_STAGES = 9
 # "semantics", "opacities", "scales", "rotations", "colors_precomp", "cov3D_precomp".  When set, the backward
 # writes those gradients straight into the given tensors (e.g. slices of one flat all-reduce buffer, see
 # goi_b200/view_parallel.py) instead of fresh allocations -- no packing copy before the collective.
+# With accumulate=True the library ADDS each view's parameter gradients to what the arena already holds
+# (goi_bwd_out.accumulate): several views per rank summed in place, one all-reduce at the end.
 grad_arena = None
+grad_accumulate = False
 
 
-def set_grad_arena(arena):
-    global grad_arena
+def set_grad_arena(arena, accumulate=False):
+    global grad_arena, grad_accumulate
     grad_arena = arena
+    grad_accumulate = bool(accumulate) and arena is not None
 
 
 def _grad_out(name, shape, f32):
@@ -285,6 +290,12 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, 
         dL_dconic = torch.empty((P, 2, 2), **f32)
         dL_dopacity = _grad_out("opacities", (P, 1), f32)
         has_sh, has_scale = g.shs is not None, g.scales is not None
+        # in-place accumulation only when EVERY input gradient of this call lives in the arena
+        need = ["means3D", "opacities"] + (["semantics"] if S else []) + (["sh"] if has_sh else ["colors_precomp"]) \
+            + (["scales", "rotations"] if has_scale else ["cov3D_precomp"])
+        acc = int(grad_accumulate and all(n in grad_arena for n in need))
+        if grad_accumulate and not acc:
+            raise RuntimeError(f"gradient accumulation needs arena slots for {need}")
         dL_dcov3D = _grad_out("cov3D_precomp", (P, 6), f32) if not has_scale else torch.empty((P, 6), **f32)
         dL_dsh = _grad_out("sh", (P, M, 3), f32) if has_sh else torch.zeros((P, M, 3), **f32)
         dL_dscales = _grad_out("scales", (P, 3), f32) if has_scale else torch.zeros((P, 3), **f32)
@@ -293,7 +304,7 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, 
             gin = goi_bwd_in(_ptr(gc), _ptr(gs_), _ptr(gd), _ptr(ga), _ptr(alphas), _ptr(radii))
             gout = goi_bwd_out(_ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors),
                                _ptr(dL_dsemantics), _ptr(dL_ddepths), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
-                               _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
+                               _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), acc, 0)
             _check(L.goi_backward(C.byref(view), C.byref(g), int(R), C.byref(gin), C.byref(gout),
                                   geomBuffer.data_ptr(), _ptr(binningBuffer), imageBuffer.data_ptr(),
                                   _stream(dev)), "goi_backward")

@@ -70,14 +70,24 @@ class GradArena:
             self.slots[name] = self.flat[off:off + p.numel()]
             off += p.numel()
 
+        self.accumulate = False
+
+    def accumulating(self, on: bool = True):
+        """`with arena.accumulating(v > 0):` -- the backward inside ADDS its parameter gradients to the arena
+        (goi_bwd_out.accumulate) instead of overwriting it: view 0 of a batch overwrites, views 1.. add, and
+        one all-reduce follows the last view (BASELINE config 4: 8 views per GPU per step)."""
+        self.accumulate = bool(on)
+        return self
+
     def __enter__(self):
         from diff_gaussian_rasterization import _C
-        _C.set_grad_arena(self.slots)
+        _C.set_grad_arena(self.slots, accumulate=self.accumulate)
         return self
 
     def __exit__(self, *exc):
         from diff_gaussian_rasterization import _C
         _C.set_grad_arena(None)
+        self.accumulate = False
         return False
 
     def clear_grads(self):

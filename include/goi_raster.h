@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GOI_ABI_VERSION 1
+#define GOI_ABI_VERSION 2
 #define GOI_MAX_SEM 64          /* largest supported semantic channel count */
 #define GOI_TILE 16             /* tile edge in pixels (config.h:16-17 BLOCK_X/Y) */
 
@@ -118,7 +118,15 @@ typedef struct goi_bwd_in {
 /* Gradient outputs (rasterizer.h:107-117).  The library zero-initialises and
  * fully writes every non-NULL array (the reference needs 11 torch::zeros
  * first, rasterize_points.cu:252-262).  dL_dsh / dL_dscale / dL_drot /
- * dL_dcov3D may be NULL when the matching input was not given. */
+ * dL_dcov3D may be NULL when the matching input was not given.
+ * accumulate != 0: the gradients of the per-Gaussian INPUTS (dL_dmean3D,
+ * dL_dsh, dL_dsemantic, dL_dopacity, dL_dscale, dL_drot, and dL_dcolor /
+ * dL_dcov3D when colors_precomp / cov3D_precomp were the inputs) are ADDED to
+ * what the arrays already hold -- several views summed in place into one
+ * buffer, the operand of the data-parallel all-reduce -- instead of being
+ * overwritten; dL_dmean2D and the scratch arrays are per-view either way.
+ * (The reference gets the same sum from autograd's accumulate-add of freshly
+ * allocated per-view gradients, diff_gaussian_rasterization/__init__.py:176.) */
 typedef struct goi_bwd_out {
     float* dL_dmean2D;          /* [P,3] (z stays 0)                           */
     float* dL_dconic;           /* [P,4] scratch (x,y,-,w) = reference [P,2,2] */
@@ -131,6 +139,8 @@ typedef struct goi_bwd_out {
     float* dL_dsh;              /* [P,M,3]                                     */
     float* dL_dscale;           /* [P,3]                                       */
     float* dL_drot;             /* [P,4]                                       */
+    int32_t accumulate;         /* bool, see above                             */
+    int32_t _pad;
 } goi_bwd_out;
 
 /* Scratch allocator callback: the C form of the reference's

@@ -19,6 +19,12 @@ from goi_b200.scenes import SyntheticCamera, SyntheticGaussians, make_loss_weigh
 pytestmark = pytest.mark.gpu
 
 
+def _yaw(deg):
+    a = math.radians(deg)
+    c, s = math.cos(a), math.sin(a)
+    return torch.tensor([[c, 0, s, 0], [0, 1, 0, 0], [-s, 0, c, 0], [0, 0, 0, 1.0]])
+
+
 def _ref_ok(S):
     from oracle import refshim
     return refshim.available(S)
@@ -240,3 +246,61 @@ def test_full_size_payload_linearity_and_euler(big_scene):
     L = float((out["semantics"].double() * w["semantics"].double()).sum())
     euler = float((g.get_semantics.double() * out["grads"]["dL_dsemantics"].double()).sum())
     assert abs(L - euler) <= 1e-3 * max(abs(L), 1.0), (L, euler)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient accumulation over views (goi_bwd_out.accumulate): the in-place sum the all-reduce operates on
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_sh,use_cov,S", [(True, False, 16), (False, True, 5), (True, False, 0)])
+def test_accumulate_mode_sums_views_in_place(use_sh, use_cov, S):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from goi_b200 import view_parallel as vp
+    P, W, H = 5000, 160, 112
+    g, cam0, bg = make_scene(P, W, H, S, 21)
+    g = g.to("cuda")
+    bg = bg.cuda()
+    cams = [SyntheticCamera(W, H, math.radians(60.0), _yaw(a), device="cuda") for a in (0.0, 2.0, -3.0)]
+    ws = [make_loss_weights(S, W, H, 30 + i, device="cuda") for i in range(3)]
+    params = {"means3D": g.get_xyz.clone().requires_grad_(True), "opacities": g.get_opacity.clone().requires_grad_(True)}
+    if S:
+        params["semantics"] = g.get_semantics.clone().requires_grad_(True)
+    if use_sh:
+        params["sh"] = g.get_features.clone().requires_grad_(True)
+    else:
+        params["colors_precomp"] = torch.sigmoid(g.get_features[:, 0, :]).contiguous().requires_grad_(True)
+    if use_cov:
+        params["cov3D_precomp"] = g.get_covariance(1.0).contiguous().requires_grad_(True)
+    else:
+        params["scales"] = g.get_scaling.clone().requires_grad_(True)
+        params["rotations"] = g.get_rotation.clone().requires_grad_(True)
+
+    def one_view(cam, w):
+        settings = GaussianRasterizationSettings(H, W, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), bg, 1.0,
+                                                 cam.world_view_transform, cam.full_proj_transform, 3,
+                                                 cam.camera_center, False, False)
+        kw = dict(means3D=params["means3D"], means2D=torch.zeros_like(params["means3D"], requires_grad=True),
+                  opacities=params["opacities"], semantics=params.get("semantics"), shs=params.get("sh"),
+                  colors_precomp=params.get("colors_precomp"), scales=params.get("scales"),
+                  rotations=params.get("rotations"), cov3D_precomp=params.get("cov3D_precomp"))
+        color, sem, radii, depth, alpha = GaussianRasterizer(settings)(**kw)
+        outs, gr = [color, depth, alpha], [w["render"], w["depth"], w["alpha"]]
+        if S:
+            outs.append(sem); gr.append(w["semantics"])
+        torch.autograd.backward(outs, gr)
+
+    # expected: autograd's own accumulate-add of three independent backward passes
+    for cam, w in zip(cams, ws):
+        one_view(cam, w)
+    expected = {k: p.grad.clone() for k, p in params.items()}
+    # in-place: view 0 overwrites the arena, views 1.. add to it
+    arena = vp.GradArena(params)
+    arena.flat.fill_(float("nan"))               # view 0 must not depend on the previous contents
+    for v, (cam, w) in enumerate(zip(cams, ws)):
+        arena.clear_grads()
+        with arena.accumulating(v > 0):
+            one_view(cam, w)
+    for k, p in params.items():
+        assert p.grad.data_ptr() == arena.slots[k].data_ptr(), f"{k}: .grad does not alias the arena"
+        scale = float(expected[k].abs().max()) or 1.0
+        err = float((arena.slots[k].view_as(expected[k]) - expected[k]).abs().max())
+        assert err <= 1e-4 * scale, f"{k}: accumulated gradient differs by {err / scale:.2e} of max"
