@@ -112,6 +112,7 @@ GeomState carve_geom(char* base, int P, int S)
     g.sortp_temp_bytes = sort_temp_bytes_for(P);
     obtain(c, g.sortp_temp, g.sortp_temp_bytes);
     obtain(c, g.rect, Pn);
+    obtain(c, g.dopacity, Pn);
     g.scan_temp_bytes = scan_temp_bytes_for(P);
     obtain(c, g.scan_temp, g.scan_temp_bytes);
     g.total_bytes = (size_t)(c - base) + 256;
@@ -169,6 +170,11 @@ static int validate(const goi_view* v, const goi_gaussians* g, bool need_opacity
         return fail(GOI_ERR_INVALID_ARG, "background/viewmatrix/projmatrix/cam_pos are required device pointers");
     if (g->rotations && (reinterpret_cast<uintptr_t>(g->rotations) & 15))
         return fail(GOI_ERR_INVALID_ARG, "rotations must be 16-byte aligned");
+    if (g->raw_flags & ~(GOI_RAW_OPACITY | GOI_RAW_SCALE | GOI_RAW_ROTATION))
+        return fail(GOI_ERR_INVALID_ARG, "unknown raw_flags bits 0x%x", g->raw_flags);
+    if ((g->raw_flags & (GOI_RAW_SCALE | GOI_RAW_ROTATION)) && !g->scales)
+        return fail(GOI_ERR_INVALID_ARG, "GOI_RAW_SCALE / GOI_RAW_ROTATION need scales + rotations");
+    if (g->shs_rest && (!g->shs || g->M < 2)) return fail(GOI_ERR_INVALID_ARG, "shs_rest needs shs (the DC block) and M >= 2");
     return GOI_OK;
 }
 
@@ -338,6 +344,7 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
         !out->dL_dmean3D || (g->S > 0 && !out->dL_dsemantic))
         return fail(GOI_ERR_INVALID_ARG, "required gradient outputs are NULL");
     if (g->shs && !out->dL_dsh) return fail(GOI_ERR_INVALID_ARG, "dL_dsh is NULL but SHs were given");
+    if (g->shs_rest && !out->dL_dsh_rest) return fail(GOI_ERR_INVALID_ARG, "dL_dsh_rest is NULL but shs_rest was given");
     if (g->scales && (!out->dL_dscale || !out->dL_drot || !out->dL_dcov3D))
         return fail(GOI_ERR_INVALID_ARG, "dL_dscale/dL_drot/dL_dcov3D are NULL but scales were given");
     if (!geom_buf || !image_buf || (num_rendered > 0 && !binning_buf)) return fail(GOI_ERR_INVALID_ARG, "scratch blobs are NULL");
@@ -354,7 +361,14 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
     stage_begin(ST_ZERO, st);
     GOI_CUDA(cudaMemsetAsync(out->dL_dmean2D, 0, sizeof(float) * 3 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_dconic, 0, sizeof(float) * 4 * P, st), "zero grads");
-    if (!acc) GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
+    // raw (logit) opacities: the composite accumulates dL/d(sigmoid) of THIS view in the geometry blob and
+    // k_preprocess_bwd applies sigmoid' while writing / adding to dL_dopacity
+    const bool raw_op = (g->raw_flags & GOI_RAW_OPACITY) != 0;
+    goi_bwd_out o2 = *out;
+    if (raw_op) {
+        o2.dL_dopacity = gs.dopacity;
+        GOI_CUDA(cudaMemsetAsync(gs.dopacity, 0, sizeof(float) * P, st), "zero grads");
+    } else if (!acc) GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
     if (!acc || g->colors_precomp == nullptr)
         GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
     GOI_CUDA(cudaMemsetAsync(out->dL_ddepth, 0, sizeof(float) * P, st), "zero grads");
@@ -363,7 +377,7 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
 
     if (num_rendered > 0) {
         StageScope sc(ST_COMPOSITE_BWD, st);
-        GOI_CUDA(launch_composite_bwd(*view, *g, *in, *out, gs, bs.vals[0], is, st), "composite backward");
+        GOI_CUDA(launch_composite_bwd(*view, *g, *in, o2, gs, bs.vals[0], is, st), "composite backward");
     }
     if ((rc = debug_sync(view, st, "composite backward")) != GOI_OK) return rc;
     { StageScope sc(ST_PREPROCESS_BWD, st); GOI_CUDA(launch_preprocess_bwd(*view, *g, *in, *out, gs, st), "preprocess backward"); }

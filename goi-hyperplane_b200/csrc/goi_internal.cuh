@@ -37,6 +37,7 @@ struct GeomState {
     char*     sortp_temp;        // CUB temp of the per-Gaussian depth sort
     size_t    sortp_temp_bytes;
     uint2*    rect;              // [P]
+    float*    dopacity;          // [P]   dL/d(activated opacity) of one view when opacities are raw logits
     Meta*     meta;
     char*     scan_temp;
     size_t    scan_temp_bytes;

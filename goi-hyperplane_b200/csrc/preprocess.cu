@@ -169,9 +169,103 @@ __device__ __forceinline__ void sh_tile_store(float* __restrict__ dst, const flo
     }
 }
 
+// Split form (GOI_RAW: shs = _features_dc [P,1,3], shs_rest = _features_rest [P,M-1,3], the two tensors
+// scene/gaussian_model.py stores): the same padded tile is filled from / drained to the two contiguous
+// blocks of the warp's 32 Gaussians, so torch.cat((dc, rest), 1) and its backward never run.
+__device__ __forceinline__ void sh_tile_load_split(float* tile, const float* __restrict__ dc, const float* __restrict__ rest,
+                                                   int rows, int M, int lane)
+{
+    for (int i = lane; i < rows * 3; i += 32) tile[(i / 3) * PRE_ROWSTRIDE + (i % 3)] = dc[i];
+    const int rl = 3 * (M - 1);
+    if (rl == 45 && rows == 32 && ((reinterpret_cast<uintptr_t>(rest) & 15) == 0)) {
+        const float4* src4 = reinterpret_cast<const float4*>(rest);     // 32 x 45 floats = 360 float4
+        float4 v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int f = lane + 32 * k;
+            v[k] = (f < 360) ? src4[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int f = lane + 32 * k;
+            if (f < 360) {
+                const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int el = 4 * f + t;
+                    tile[(el / 45) * PRE_ROWSTRIDE + 3 + (el % 45)] = e[t];
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < rows * rl; i += 32) tile[(i / rl) * PRE_ROWSTRIDE + 3 + (i % rl)] = rest[i];
+    }
+}
+__device__ __forceinline__ void sh_tile_store_split(float* __restrict__ dc, float* __restrict__ rest, const float* tile,
+                                                    int rows, int M, int lane, bool acc)
+{
+    for (int i = lane; i < rows * 3; i += 32) {
+        const float v = tile[(i / 3) * PRE_ROWSTRIDE + (i % 3)];
+        dc[i] = acc ? dc[i] + v : v;
+    }
+    const int rl = 3 * (M - 1);
+    if (rl == 45 && rows == 32 && ((reinterpret_cast<uintptr_t>(rest) & 15) == 0)) {
+        float4* dst4 = reinterpret_cast<float4*>(rest);
+        float4 old[12];
+        if (acc) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int f = lane + 32 * k;
+                old[k] = (f < 360) ? dst4[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int f = lane + 32 * k;
+            if (f < 360) {
+                float e[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int el = 4 * f + t;
+                    e[t] = tile[(el / 45) * PRE_ROWSTRIDE + 3 + (el % 45)];
+                }
+                float4 v = make_float4(e[0], e[1], e[2], e[3]);
+                if (acc) { v.x += old[k].x; v.y += old[k].y; v.z += old[k].z; v.w += old[k].w; }
+                dst4[f] = v;
+            }
+        }
+    } else {
+        for (int i = lane; i < rows * rl; i += 32) {
+            const float v = tile[(i / rl) * PRE_ROWSTRIDE + 3 + (i % rl)];
+            rest[i] = acc ? rest[i] + v : v;
+        }
+    }
+}
+
+// The activations of scene/gaussian_model.py:90-117, applied while loading when the matching GOI_RAW_* bit
+// is set: torch.exp, torch.sigmoid (1 / (1 + exp(-x))), torch.nn.functional.normalize (x / max(|x|, 1e-12)).
+__device__ __forceinline__ float3 load_scale(const float* __restrict__ scales, int idx, int raw_flags)
+{
+    float3 s = make_float3(scales[3 * idx + 0], scales[3 * idx + 1], scales[3 * idx + 2]);
+    if (raw_flags & GOI_RAW_SCALE) s = make_float3(expf(s.x), expf(s.y), expf(s.z));
+    return s;
+}
+__device__ __forceinline__ float4 load_rotation(const float* __restrict__ rotations, int idx, int raw_flags, float* norm_out)
+{
+    float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+    float n = 1.f;
+    if (raw_flags & GOI_RAW_ROTATION) {
+        n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+        q = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+    }
+    if (norm_out) *norm_out = n;
+    return q;
+}
+
 __global__ void __launch_bounds__(128) k_preprocess_fwd(
     int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
+    const float* __restrict__ shs_rest, int raw_flags,
     const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
     const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int gx, int gy, int prefiltered,
@@ -218,10 +312,11 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
             for (int i = 0; i < 6; ++i) c3[i] = cov3D_precomp[6 * idx + i];
         } else {
             M3 S = m3_make(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
-            S.m[0][0] = scale_modifier * scales[3 * idx + 0];
-            S.m[1][1] = scale_modifier * scales[3 * idx + 1];
-            S.m[2][2] = scale_modifier * scales[3 * idx + 2];
-            const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+            const float3 sc = load_scale(scales, idx, raw_flags);
+            S.m[0][0] = scale_modifier * sc.x;
+            S.m[1][1] = scale_modifier * sc.y;
+            S.m[2][2] = scale_modifier * sc.z;
+            const float4 q = load_rotation(rotations, idx, raw_flags, nullptr);
             const M3 R = quat_R(q);
             const M3 Mm = m3_mul(S, R);
             const M3 Sigma = m3_mul(m3_t(Mm), Mm);
@@ -266,7 +361,8 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
         if (__any_sync(0xffffffffu, visible)) {
             const int base = blockIdx.x * blockDim.x + warp * 32;
             const int rows = min(32, P - base);
-            sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
+            if (shs_rest) sh_tile_load_split(tile, shs + (size_t)base * 3, shs_rest + (size_t)base * (rowlen - 3), rows, M, lane);
+            else sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
             __syncwarp();
         }
         if (visible) {
@@ -306,7 +402,8 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
     }
     if (!visible) return;
 
-    const float opacity = opacities[idx];
+    float opacity = opacities[idx];
+    if (raw_flags & GOI_RAW_OPACITY) opacity = 1.0f / (1.0f + expf(-opacity));
     // power_cut: a pair with power < power_cut has opacity*exp(power) < 1/255 with margin, so the
     // composite may skip it before evaluating expf (a provably non-contributing pair, never a
     // borderline one: the margin of 0.01 in the exponent is ~1e5 ulp of the decision value).
@@ -337,7 +434,7 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
     cudaMemsetAsync(gs.meta, 0, sizeof(Meta), st);
     k_preprocess_fwd<<<(P + 127) / 128, 128, 0, st>>>(
         P, v.sh_degree, g.M, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
-        g.cov3D_precomp, g.colors_precomp, v.viewmatrix, v.projmatrix, v.cam_pos, v.width, v.height,
+        g.shs_rest, g.raw_flags, g.cov3D_precomp, g.colors_precomp, v.viewmatrix, v.projmatrix, v.cam_pos, v.width, v.height,
         v.tan_fovx, v.tan_fovy, focal_x, focal_y, gx, gy, v.prefiltered, radii, gs.geo, gs.rgbd, gs.cov3D,
         gs.clamped, gs.tiles_touched, gs.rect, gs.depth_keys[0], gs.order[0], gs.meta);
     count_launches(1);
@@ -357,7 +454,9 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
     const float* __restrict__ dL_dmean2D, const float* __restrict__ dL_dconics, const float* __restrict__ dL_dcolor,
     const float* __restrict__ dL_ddepth,
     float* __restrict__ dL_dmeans, float* __restrict__ dL_dcov, float* __restrict__ dL_dsh,
-    float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int acc, int acc_cov)
+    float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int acc, int acc_cov,
+    const float* __restrict__ shs_rest, float* __restrict__ dL_dsh_rest, int raw_flags,
+    const float4* __restrict__ geo, const float* __restrict__ dopa_act, float* __restrict__ dL_dopacity)
 {
     // One warp = 32 consecutive Gaussians; their SH rows (and the dL_dsh rows) are 32 x 3M contiguous floats
     // and move through one shared-memory tile with fully coalesced global accesses.
@@ -372,7 +471,8 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
     const int rows = max(0, min(32, P - base));
 
     if (shs != nullptr && __any_sync(0xffffffffu, active)) {
-        sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
+        if (shs_rest) sh_tile_load_split(tile, shs + (size_t)base * 3, shs_rest + (size_t)base * (rowlen - 3), rows, M, lane);
+        else sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
     }
     __syncwarp();
 
@@ -558,10 +658,19 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
             }
         __syncwarp();
         // (accumulate mode: a warp whose Gaussians are all culled adds nothing -- skip the read-modify-write)
-        if (!acc || __any_sync(0xffffffffu, active))
-            sh_tile_store(dL_dsh + (size_t)base * rowlen, tile, rows, rowlen, lane, acc != 0);
+        if (!acc || __any_sync(0xffffffffu, active)) {
+            if (shs_rest) sh_tile_store_split(dL_dsh + (size_t)base * 3, dL_dsh_rest + (size_t)base * (rowlen - 3), tile, rows, M, lane, acc != 0);
+            else sh_tile_store(dL_dsh + (size_t)base * rowlen, tile, rows, rowlen, lane, acc != 0);
+        }
     }
     if (!in_range) return;
+    if (dopa_act != nullptr) {
+        // raw opacities: d sigmoid(x)/dx = o (1 - o); the composite left dL/do of this view in dopa_act
+        float v = 0.f;
+        if (active) { const float o = geo[2 * (size_t)idx + 1].y; v = dopa_act[idx] * (o * (1.f - o)); }
+        if (!acc) dL_dopacity[idx] = v;
+        else if (active) dL_dopacity[idx] += v;
+    }
     if (acc) {
         if (!active) return;                  // zero contribution
         dL_dmeans[3 * idx] += gmean.x; dL_dmeans[3 * idx + 1] += gmean.y; dL_dmeans[3 * idx + 2] += gmean.z;
@@ -578,12 +687,13 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
         float3 dsc = make_float3(0.f, 0.f, 0.f);
         float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
-            const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+            float qnorm;
+            const float4 q = load_rotation(rotations, idx, raw_flags, &qnorm);
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             const M3 R = quat_R(q);
             M3 S = m3_make(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
-            const float3 s = make_float3(scale_modifier * scales[3 * idx], scale_modifier * scales[3 * idx + 1],
-                                         scale_modifier * scales[3 * idx + 2]);
+            const float3 sact = load_scale(scales, idx, raw_flags);
+            const float3 s = make_float3(scale_modifier * sact.x, scale_modifier * sact.y, scale_modifier * sact.z);
             S.m[0][0] = s.x; S.m[1][1] = s.y; S.m[2][2] = s.z;
             const M3 Mm = m3_mul(S, R);
             const M3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2],
@@ -606,6 +716,13 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
             dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
             dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
             dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+            // chain through the fused activations (gradients w.r.t. the stored parameters)
+            if (raw_flags & GOI_RAW_SCALE) { dsc.x *= sact.x; dsc.y *= sact.y; dsc.z *= sact.z; }          // d exp
+            if (raw_flags & GOI_RAW_ROTATION) {                                  // d (q/|q|): (I - qh qh^T) dq / |q|
+                const float dt = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w;
+                dq = make_float4((dq.x - q.x * dt) / qnorm, (dq.y - q.y * dt) / qnorm, (dq.z - q.z * dt) / qnorm,
+                                 (dq.w - q.w * dt) / qnorm);
+            }
         }
         if (acc) {
             dsc.x += dL_dscale[3 * idx + 0]; dsc.y += dL_dscale[3 * idx + 1]; dsc.z += dL_dscale[3 * idx + 2];
@@ -630,7 +747,9 @@ cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, con
         out.dL_dmean2D, out.dL_dconic, out.dL_dcolor, out.dL_ddepth,
         out.dL_dmean3D, out.dL_dcov3D, g.shs ? out.dL_dsh : nullptr,
         g.scales ? out.dL_dscale : nullptr, g.scales ? out.dL_drot : nullptr, out.accumulate != 0,
-        out.accumulate != 0 && g.cov3D_precomp != nullptr);
+        out.accumulate != 0 && g.cov3D_precomp != nullptr,
+        g.shs ? g.shs_rest : nullptr, out.dL_dsh_rest, g.raw_flags, gs.geo,
+        (g.raw_flags & GOI_RAW_OPACITY) ? gs.dopacity : nullptr, out.dL_dopacity);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -25,9 +25,10 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GOI_RASTER_LIB", os.path.join(_HERE, "..", "lib", "libgoi_raster.so"))
-GOI_ABI_VERSION = 2
+GOI_ABI_VERSION = 3
 GOI_MAX_SEM = 64
 GOI_MASK_APE, GOI_MASK_OSH = 0, 1
+GOI_RAW_OPACITY, GOI_RAW_SCALE, GOI_RAW_ROTATION = 1, 2, 4
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -40,9 +41,10 @@ class goi_view(C.Structure):
 
 
 class goi_gaussians(C.Structure):
-    _fields_ = [("P", C.c_int32), ("M", C.c_int32), ("S", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("P", C.c_int32), ("M", C.c_int32), ("S", C.c_int32), ("raw_flags", C.c_int32),
                 ("means3D", _f32p), ("shs", _f32p), ("colors_precomp", _f32p), ("semantics", _f32p),
-                ("opacities", _f32p), ("scales", _f32p), ("rotations", _f32p), ("cov3D_precomp", _f32p)]
+                ("opacities", _f32p), ("scales", _f32p), ("rotations", _f32p), ("cov3D_precomp", _f32p),
+                ("shs_rest", _f32p)]
 
 
 class goi_fwd_out(C.Structure):
@@ -59,7 +61,7 @@ class goi_bwd_out(C.Structure):
     _fields_ = [("dL_dmean2D", _f32p), ("dL_dconic", _f32p), ("dL_dopacity", _f32p), ("dL_dcolor", _f32p),
                 ("dL_dsemantic", _f32p), ("dL_ddepth", _f32p), ("dL_dmean3D", _f32p), ("dL_dcov3D", _f32p),
                 ("dL_dsh", _f32p), ("dL_dscale", _f32p), ("dL_drot", _f32p), ("accumulate", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("_pad", C.c_int32), ("dL_dsh_rest", _f32p)]
 
 
 class goi_mask_args(C.Structure):
@@ -197,33 +199,41 @@ def _make_view(bg, viewmatrix, projmatrix, campos, W, H, tan_fovx, tan_fovy, sca
                     _ptr(campos))
 
 
-def _make_gaussians(means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp, keep):
+def _make_gaussians(means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp, keep, raw_flags=0,
+                    sh_rest=None):
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")      # rasterize_points.cu:58-60
     means3D = _f32(means3D, "means3D") if means3D.numel() else means3D
     sh, colors, semantics = _f32(sh, "sh"), _f32(colors, "colors_precomp"), _f32(semantics, "semantics")
     opacity, scales = _f32(opacity, "opacities"), _f32(scales, "scales")
     rotations, cov3D_precomp = _f32(rotations, "rotations"), _f32(cov3D_precomp, "cov3D_precomp")
-    keep += [means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp]
+    sh_rest = _f32(sh_rest, "sh_rest")
+    keep += [means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp, sh_rest]
     P = means3D.shape[0]
     M = sh.shape[1] if sh is not None else 0
+    if sh_rest is not None:
+        if sh is None or sh.shape[1] != 1:
+            raise RuntimeError("sh_rest needs sh = the DC block [P,1,3]")
+        M = 1 + sh_rest.shape[1]
     S = semantics.shape[1] if semantics is not None else 0
     if semantics is not None and (semantics.ndim != 2 or semantics.shape[0] != P):
         raise RuntimeError("semantics must have dimensions (num_points, S)")
-    g = goi_gaussians(P, M, S, 0, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(semantics), _ptr(opacity),
-                      _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp))
+    g = goi_gaussians(P, M, S, int(raw_flags), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(semantics), _ptr(opacity),
+                      _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp), _ptr(sh_rest))
     return g, means3D
 
 
 def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug):
-    """RasterizeGaussiansCUDA (reference rasterize_points.cu:35-123)."""
+                        prefiltered, debug, raw_flags=0, sh_rest=None):
+    """RasterizeGaussiansCUDA (reference rasterize_points.cu:35-123).  raw_flags / sh_rest (not in the
+    reference): the inputs are the STORED parameters and the library applies the activations (GOI_RAW_*)."""
     L = lib()
     keep = []
     dev = means3D.device
     with torch.cuda.device(dev):
-        g, means3D = _make_gaussians(means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp, keep)
+        g, means3D = _make_gaussians(means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp, keep,
+                                     raw_flags, sh_rest)
         view = _make_view(bg, viewmatrix, projmatrix, campos, image_width, image_height, tan_fovx, tan_fovy,
                           scale_modifier, degree, prefiltered, debug, keep)
         P, S, H, W = g.P, g.S, int(image_height), int(image_width)
@@ -265,13 +275,15 @@ def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotatio
 def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_semantic, dL_dout_depth, dL_dout_alpha, sh, degree, campos, geomBuffer, R,
-                                 binningBuffer, imageBuffer, alphas, debug):
-    """RasterizeGaussiansBackwardCUDA (reference rasterize_points.cu:213-306)."""
+                                 binningBuffer, imageBuffer, alphas, debug, raw_flags=0, sh_rest=None):
+    """RasterizeGaussiansBackwardCUDA (reference rasterize_points.cu:213-306).  With sh_rest the SH gradient
+    comes back as the pair (dL_dsh_dc [P,1,3], dL_dsh_rest [P,M-1,3]) in place of dL_dsh."""
     L = lib()
     keep = []
     dev = means3D.device
     with torch.cuda.device(dev):
-        g, means3D = _make_gaussians(means3D, sh, colors, semantics, None, scales, rotations, cov3D_precomp, keep)
+        g, means3D = _make_gaussians(means3D, sh, colors, semantics, None, scales, rotations, cov3D_precomp, keep,
+                                     raw_flags, sh_rest)
         H, W = int(alphas.shape[-2]), int(alphas.shape[-1])
         view = _make_view(bg, viewmatrix, projmatrix, campos, W, H, tan_fovx, tan_fovy, scale_modifier, degree,
                           False, debug, keep)
@@ -292,22 +304,31 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, 
         has_sh, has_scale = g.shs is not None, g.scales is not None
         # in-place accumulation only when EVERY input gradient of this call lives in the arena
         need = ["means3D", "opacities"] + (["semantics"] if S else []) + (["sh"] if has_sh else ["colors_precomp"]) \
+            + (["sh_rest"] if sh_rest is not None and sh_rest.numel() else []) \
             + (["scales", "rotations"] if has_scale else ["cov3D_precomp"])
         acc = int(grad_accumulate and all(n in grad_arena for n in need))
         if grad_accumulate and not acc:
             raise RuntimeError(f"gradient accumulation needs arena slots for {need}")
         dL_dcov3D = _grad_out("cov3D_precomp", (P, 6), f32) if not has_scale else torch.empty((P, 6), **f32)
-        dL_dsh = _grad_out("sh", (P, M, 3), f32) if has_sh else torch.zeros((P, M, 3), **f32)
+        split = g.shs_rest is not None
+        dL_dsh_rest = None
+        if split:
+            dL_dsh = _grad_out("sh", (P, 1, 3), f32)
+            dL_dsh_rest = _grad_out("sh_rest", (P, M - 1, 3), f32)
+        else:
+            dL_dsh = _grad_out("sh", (P, M, 3), f32) if has_sh else torch.zeros((P, M, 3), **f32)
         dL_dscales = _grad_out("scales", (P, 3), f32) if has_scale else torch.zeros((P, 3), **f32)
         dL_drotations = _grad_out("rotations", (P, 4), f32) if has_scale else torch.zeros((P, 4), **f32)
         if P != 0:
             gin = goi_bwd_in(_ptr(gc), _ptr(gs_), _ptr(gd), _ptr(ga), _ptr(alphas), _ptr(radii))
             gout = goi_bwd_out(_ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors),
                                _ptr(dL_dsemantics), _ptr(dL_ddepths), _ptr(dL_dmeans3D), _ptr(dL_dcov3D),
-                               _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), acc, 0)
+                               _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), acc, 0, _ptr(dL_dsh_rest))
             _check(L.goi_backward(C.byref(view), C.byref(g), int(R), C.byref(gin), C.byref(gout),
                                   geomBuffer.data_ptr(), _ptr(binningBuffer), imageBuffer.data_ptr(),
                                   _stream(dev)), "goi_backward")
+    if split:
+        dL_dsh = (dL_dsh, dL_dsh_rest)
     return (dL_dmeans2D, dL_dcolors, dL_dsemantics, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
             dL_drotations)
 

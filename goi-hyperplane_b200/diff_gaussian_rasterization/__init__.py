@@ -128,6 +128,49 @@ class _RasterizeGaussians(torch.autograd.Function):
         return color, gau_sem, num_gsem
 
 
+class _RasterizeGaussiansRaw(torch.autograd.Function):
+    """Not in the reference: the same rasterization taking the STORED parameters of
+    scene/gaussian_model.py -- opacity logits, log-scales, un-normalised quaternions, SH split into
+    _features_dc / _features_rest -- with sigmoid / exp / normalize / cat (get_opacity, get_scaling,
+    get_rotation, get_features, :90-117) and their derivatives fused into the per-Gaussian kernels."""
+
+    RAW = _C.GOI_RAW_OPACITY | _C.GOI_RAW_SCALE | _C.GOI_RAW_ROTATION
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, features_dc, features_rest, semantics, opacity_logits, log_scales,
+                raw_rotations, raster_settings):
+        empty = torch.Tensor([])
+        rs = raster_settings
+        (num_rendered, color, semant, depth, alpha, radii, geomBuffer, binningBuffer, imgBuffer) = \
+            _C.rasterize_gaussians(rs.bg, means3D, empty, semantics, opacity_logits, log_scales, raw_rotations,
+                                   rs.scale_modifier, empty, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+                                   rs.image_height, rs.image_width, features_dc, rs.sh_degree, rs.campos,
+                                   rs.prefiltered, rs.debug, raw_flags=_RasterizeGaussiansRaw.RAW,
+                                   sh_rest=features_rest)
+        ctx.raster_settings, ctx.num_rendered, ctx.opacity_shape = rs, num_rendered, opacity_logits.shape
+        ctx.save_for_backward(semantics, means3D, log_scales, raw_rotations, radii, features_dc, features_rest,
+                              geomBuffer, binningBuffer, imgBuffer, alpha)
+        ctx.mark_non_differentiable(radii)
+        return color, semant, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_sem, grad_out_radii, grad_depth, grad_alpha):
+        rs = ctx.raster_settings
+        (semantics, means3D, log_scales, raw_rotations, radii, features_dc, features_rest, geomBuffer, binningBuffer,
+         imgBuffer, alpha) = ctx.saved_tensors
+        empty = torch.Tensor([])
+        (grad_means2D, _gc, grad_semantics, grad_opacities, grad_means3D, _gcov, grad_sh, grad_scales,
+         grad_rotations) = _C.rasterize_gaussians_backward(
+            rs.bg, means3D, radii, empty, semantics, log_scales, raw_rotations, rs.scale_modifier, empty,
+            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_out_sem, grad_depth,
+            grad_alpha, features_dc, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer,
+            alpha, rs.debug, raw_flags=_RasterizeGaussiansRaw.RAW, sh_rest=features_rest)
+        grad_dc, grad_rest = grad_sh
+        return (grad_means3D, grad_means2D, grad_dc.view(features_dc.shape), grad_rest.view(features_rest.shape),
+                grad_semantics if semantics.numel() else None, grad_opacities.view(ctx.opacity_shape),
+                grad_scales, grad_rotations, None)
+
+
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
     image_width: int
@@ -181,6 +224,16 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, semantics, opacities, scales, rotations,
                                    cov3D_precomp, raster_settings)
+
+    def forward_raw(self, means3D, means2D, opacity_logits, features_dc, features_rest, log_scales, raw_rotations,
+                    semantics=None):
+        """Same outputs as ``forward`` from the STORED parameters (activations fused into the kernels):
+        equals forward(means3D, means2D, sigmoid(opacity_logits), shs=cat((features_dc, features_rest), 1),
+        semantics=semantics, scales=exp(log_scales), rotations=normalize(raw_rotations))."""
+        if semantics is None:
+            semantics = torch.Tensor([])
+        return _RasterizeGaussiansRaw.apply(means3D, means2D, features_dc, features_rest, semantics, opacity_logits,
+                                            log_scales, raw_rotations, self.raster_settings)
 
     def trace(self, means3D, means2D, opacities, shs=None, colors_precomp=None, img_sem=None, scales=None,
               rotations=None, cov3D_precomp=None):

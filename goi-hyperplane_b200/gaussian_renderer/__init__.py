@@ -82,8 +82,15 @@ def _marshal(viewpoint_camera, pc, pipe, scaling_modifier, override_color):
     return scales, rotations, cov3D_precomp, shs, colors_precomp
 
 
-def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
-    """Render the scene (reference :18-105).  Background tensor (bg_color) must be on GPU!"""
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+           fused_activations=False):
+    """Render the scene (reference :18-105).  Background tensor (bg_color) must be on GPU!
+
+    fused_activations=True (opt-in, not in the reference) hands the model's STORED
+    parameters (``pc._opacity, _scaling, _rotation, _features_dc, _features_rest``) to the rasterizer, which
+    applies sigmoid / exp / normalize / cat while loading them -- same images, gradients w.r.t. the stored
+    parameters, none of the per-render activation kernels and no 384 B/Gaussian SH concatenation.  It needs the
+    default pipeline (no override_color, no compute_cov3D_python / convert_SHs_python, no semantic masks)."""
     screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True,
                                           device=pc.get_xyz.device) + 0
     try:
@@ -91,6 +98,17 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     except Exception:
         pass
     rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, pc, pipe, bg_color, scaling_modifier))
+    if fused_activations:
+        if override_color is not None or pipe.compute_cov3D_python or pipe.convert_SHs_python:
+            raise ValueError("fused_activations needs the default pipeline (SH colours, scale/rotation covariance)")
+        if getattr(pc, "_semantics_masks", None) is not None:
+            raise ValueError("fused_activations does not apply semantic masks; call set_semantic_masks(None)")
+        rendered_image, rendered_sem, radii, depth, alpha = rasterizer.forward_raw(
+            means3D=pc._xyz, means2D=screenspace_points, opacity_logits=pc._opacity, features_dc=pc._features_dc,
+            features_rest=pc._features_rest, log_scales=pc._scaling, raw_rotations=pc._rotation,
+            semantics=pc._semantics)
+        return {"render": rendered_image, "semantics": rendered_sem, "depth": depth, "alpha": alpha,
+                "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}
     scales, rotations, cov3D_precomp, shs, colors_precomp = _marshal(viewpoint_camera, pc, pipe, scaling_modifier,
                                                                      override_color)
     rendered_image, rendered_sem, radii, depth, alpha = rasterizer(

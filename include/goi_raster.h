@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GOI_ABI_VERSION 2
+#define GOI_ABI_VERSION 3
 #define GOI_MAX_SEM 64          /* largest supported semantic channel count */
 #define GOI_TILE 16             /* tile edge in pixels (config.h:16-17 BLOCK_X/Y) */
 
@@ -82,16 +82,34 @@ typedef struct goi_gaussians {
     int32_t P;                  /* number of Gaussians                         */
     int32_t M;                  /* SH coefficients per colour (sh.size(1))     */
     int32_t S;                  /* semantic channels (0 = none)                */
-    int32_t _pad;
+    int32_t raw_flags;          /* GOI_RAW_* bits, 0 = the reference contract  */
     const float* means3D;       /* [P,3]                                       */
-    const float* shs;           /* [P,M,3] or NULL                             */
+    const float* shs;           /* [P,M,3] or NULL ([P,1,3] when shs_rest set) */
     const float* colors_precomp;/* [P,3]   or NULL                             */
     const float* semantics;     /* [P,S]   or NULL iff S==0                    */
     const float* opacities;     /* [P]                                         */
     const float* scales;        /* [P,3]   or NULL                             */
     const float* rotations;     /* [P,4]   or NULL                             */
     const float* cov3D_precomp; /* [P,6]   or NULL                             */
+    const float* shs_rest;      /* [P,M-1,3] or NULL: SH split as the model stores it */
 } goi_gaussians;
+
+/* raw_flags: the caller hands over the STORED parameters of
+ * scene/gaussian_model.py and the library applies the activations of its
+ * getters (:90-117) while loading them -- and their derivatives in the
+ * backward, so the gradients come back w.r.t. the stored parameters:
+ *   GOI_RAW_OPACITY   opacities = logits;  sigmoid          (get_opacity, :115-117)
+ *   GOI_RAW_SCALE     scales = log-scales; exp              (get_scaling, :90-92)
+ *   GOI_RAW_ROTATION  rotations un-normalised; q / max(|q|, 1e-12)
+ *                                                           (get_rotation, :94-96)
+ * and shs_rest != NULL replaces torch.cat((features_dc, features_rest), 1)
+ * (get_features, :102-106): shs = _features_dc [P,1,3], shs_rest =
+ * _features_rest [P,M-1,3].  The reference pays one elementwise kernel per
+ * activation plus a 384 B/Gaussian concatenation copy on EVERY render (and the
+ * matching autograd nodes in the backward); here they cost nothing extra. */
+#define GOI_RAW_OPACITY  1
+#define GOI_RAW_SCALE    2
+#define GOI_RAW_ROTATION 4
 
 /* Forward outputs (rasterizer.h:58-62).  All pixels / all P entries are
  * written by the library; the caller need not zero-fill (the reference glue
@@ -141,6 +159,7 @@ typedef struct goi_bwd_out {
     float* dL_drot;             /* [P,4]                                       */
     int32_t accumulate;         /* bool, see above                             */
     int32_t _pad;
+    float* dL_dsh_rest;         /* [P,M-1,3] when shs_rest was given (dL_dsh is then [P,1,3]) */
 } goi_bwd_out;
 
 /* Scratch allocator callback: the C form of the reference's
