@@ -35,25 +35,6 @@ namespace goi {
 
 constexpr int RSTRIDE = 36;      // floats per 32-pixel row in shared memory: float4-aligned, conflict-free
 
-// Transposing butterfly over the 8 lanes that share lane bits 3..4 (xor 4, 2, 1): every lane holds 8
-// partial values v[0..7]; afterwards v[0] of the lane with (lane & 7) == u is the 8-lane sum of value u.
-// 7 shuffles instead of 8 x 3.
-__device__ __forceinline__ float group8_transpose_reduce(float (&v)[8], int lane)
-{
-#pragma unroll
-    for (int off = 4, n = 8; off >= 1; off >>= 1, n >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int k = 0; k < n / 2; ++k) {
-            const float a = v[k], b = v[k + n / 2];
-            const float send = upper ? a : b;
-            const float keep = upper ? b : a;
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
-
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp: x = 1 - alpha is in [0.01, 1]
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -85,7 +66,10 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     float4* s_g1 = smem + 2 * BATCH;                   // [2][BATCH]
     float4* s_pay = smem + 4 * BATCH;                  // [2][BATCH][ROW]
     float* s_red = reinterpret_cast<float*>(smem + 4 * BATCH + 2 * BATCH * ROW);   // [8 warps][2][DROWS][RSTRIDE]
-    __shared__ int s_id[2][BATCH];
+    // second stage of the reduction: [8 warps][4 value groups][VS], value u of pixel group pg at u*USTRIDE + pg
+    constexpr int USTRIDE = 12;                        // floats between values: 16-B aligned, LDS.128 conflict-free
+    constexpr int VS = NBLK * 8 * USTRIDE + 8;         // floats per value group: (VS mod 32 == 8) keeps the STS conflict-free
+    float* s_tr = s_red + 8 * 2 * DROWS * RSTRIDE;
     __shared__ uint32_t s_max_contrib;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -125,14 +109,15 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         if (dL_dpixdepth) g_depth = dL_dpixdepth[pix];
         if (dL_dpixalpha) g_alpha = dL_dpixalpha[pix];
     }
-    const float bg_dot_dpixel = bg[0] * g_rgb[0] + bg[1] * g_rgb[1] + bg[2] * g_rgb[2];
-    const float ddelx_dx = 0.5f * (float)W;         // reference: 0.5 * W (double, exact either way)
-    const float ddely_dy = 0.5f * (float)H;
+    const float nTf_bg = -T_final * (bg[0] * g_rgb[0] + bg[1] * g_rgb[1] + bg[2] * g_rgb[2]);
 
     // ---- gsel[u][k] = pixel-gradient of payload value (vg*PPG + u) at pixel 4*pg + k of this warp: the
     //      4x PPG sub-block of the warp's 32 x NPROD gradient matrix this lane multiplies the weights with.
-    //      Built once through shared memory (transpose of the per-lane rows).
-    float gsel[PPG][4];
+    //      Built once through shared memory (transpose of the per-lane rows).  Values are held as (u, u+1)
+    //      register pairs so one FFMA2 with a broadcast weight advances two dot products.
+    constexpr int NP2 = PPG / 2;                       // full value pairs; an odd last value stays scalar
+    float2 gp[NP2 > 0 ? NP2 : 1][4];
+    float gtail[4] = {0.f, 0.f, 0.f, 0.f};
     {
         float* gt = s_red + warp * (2 * DROWS * RSTRIDE);       // scratch: one value row at a time, reuse dyn rows
         __syncthreads();
@@ -150,10 +135,18 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
             }
             __syncwarp();
             const float4 t = *reinterpret_cast<const float4*>(gt + vg * RSTRIDE + 4 * pg);
-            gsel[u][0] = t.x; gsel[u][1] = t.y; gsel[u][2] = t.z; gsel[u][3] = t.w;
+            if (u < 2 * NP2) {
+                if (u & 1) { gp[u >> 1][0].y = t.x; gp[u >> 1][1].y = t.y; gp[u >> 1][2].y = t.z; gp[u >> 1][3].y = t.w; }
+                else       { gp[u >> 1][0].x = t.x; gp[u >> 1][1].x = t.y; gp[u >> 1][2].x = t.z; gp[u >> 1][3].x = t.w; }
+            } else { gtail[0] = t.x; gtail[1] = t.y; gtail[2] = t.z; gtail[3] = t.w; }
             __syncwarp();
         }
     }
+    // own-pixel gradients as (x,y) / (z,w) pairs matching the float4 payload rows
+    const float2 g01 = make_float2(g_rgb[0], g_rgb[1]), g2d = make_float2(g_rgb[2], g_depth);
+    float2 gs2[NS4 > 0 ? 2 * NS4 : 1];
+#pragma unroll
+    for (int k = 0; k < 2 * NS4; ++k) gs2[k] = make_float2(g_sem[2 * k], g_sem[2 * k + 1]);
 
     {   // the walk only needs list entries [0, max n_contrib over the tile)
         uint32_t m = last_contributor;
@@ -177,7 +170,6 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 cp_async16(&s_g0[buf * BATCH + j], &geo[2 * (size_t)id]);
                 cp_async16(&s_g1[buf * BATCH + j], &geo[2 * (size_t)id + 1]);
                 cp_async16(&s_pay[(buf * BATCH + j) * ROW], &rgbd[id]);
-                s_id[buf][j] = (int)id;
             } else {
                 float4* dst = &s_pay[(buf * BATCH + j) * ROW + 1];
                 const float* src = sem + (size_t)id * S;
@@ -212,16 +204,38 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
             else if (gv == 4) { out_ptr[k] = dL_dconic + 3; out_stride[k] = 4; }
             else if (gv == 5) { out_ptr[k] = dL_dopacity; out_stride[k] = 1; }
         }
+        if (out_ptr[k] == nullptr) out_stride[k] = 0;      // stride 0 = this lane writes nothing
     }
-    // the two geometry rows this lane's value group sums (row 0 = weights, rows 1..6 = geometry values);
-    // groups whose slot is unused (gv >= 6) read the weight row and scale by 0
-    const int grow0 = (2 * vg + 0 < 6) ? 1 + 2 * vg : 0, grow1 = (2 * vg + 1 < 6) ? 2 + 2 * vg : 0;
-    const float gsc0 = (2 * vg + 0 < 6) ? 1.f : 0.f, gsc1 = (2 * vg + 1 < 6) ? 1.f : 0.f;
+    // dL_dmean2D carries the pixel->NDC factor (0.5 W, 0.5 H; backward.cu:612-613): applied once to the reduced sum
+    float out_scale[NBLK];
+#pragma unroll
+    for (int k = 0; k < NBLK; ++k) {
+        const int u = 8 * k + pg;
+        out_scale[k] = (vg == 0 && u == PPG) ? 0.5f * (float)W : (vg == 0 && u == PPG + 1) ? 0.5f * (float)H : 1.f;
+    }
 
     float last_alpha = 0.f, last_q = 0.f, acc = 0.f;
     const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
+    // Shared-memory addresses of the per-warp reduction rows, kept in four registers (laundered through an
+    // opaque mov so the compiler does not re-derive them from %tid inside the walk):
+    //   ad      this walk's publish address (row 0, this lane's column); alternates between the two halves
+    //   ad_sum  sum of both halves' publish addresses (ad <- ad_sum - ad flips the half)
+    //   dl      ad + dl = this lane's 4-pixel group in row 0 (pg * 16 - lane * 4)
+    //   go      byte offset of the first of this value group's two geometry rows (rows 1+2vg, 2+2vg); the
+    //           fourth group has none and reads rows 0/1 into values that are never written out
     const uint32_t a_dyn = smem_u32(s_red + warp * (2 * DROWS * RSTRIDE));
-    uint32_t flip = 0;                                 // byte offset of the current half of the double buffer
+    uint32_t ad = a_dyn + lane * 4 + DROWS * RSTRIDE * 4;
+    uint32_t ad_sum = 2 * (a_dyn + lane * 4) + DROWS * RSTRIDE * 4;
+    uint32_t dl = (uint32_t)(pg * 16 - lane * 4);
+    uint32_t go = vg < 3 ? (uint32_t)((1 + 2 * vg) * RSTRIDE * 4) : 0u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(ad_sum));
+    asm volatile("mov.u32 %0, %0;" : "+r"(dl));
+    asm volatile("mov.u32 %0, %0;" : "+r"(go));
+    //   atw     this lane's column pg of value 0 in its value group of the transpose region; atr: value pg's row
+    uint32_t atw = smem_u32(s_tr + warp * (4 * VS) + vg * VS + pg);
+    uint32_t atr = smem_u32(s_tr + warp * (4 * VS) + vg * VS + pg * USTRIDE);
+    asm volatile("mov.u32 %0, %0;" : "+r"(atw));
+    asm volatile("mov.u32 %0, %0;" : "+r"(atr));
     GOI_STAT_DECL;
 
     if (nb > 0) stage(0);
@@ -257,7 +271,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 float4 s4[NS4 > 0 ? NS4 : 1];
 #pragma unroll
                 for (int k = 0; k < NS4; ++k) s4[k] = lds128(ap + 16 + 16 * k);
-                const uint32_t id = (uint32_t)s_id[buf][j];
+                const uint32_t id = (uint32_t)__float_as_int(g1.w);      // preprocess stores the index bits here
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                 const float G = expf(power);
@@ -269,63 +283,77 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 GOI_STAT_ADD(2, lane == 0 ? 1u : 0u);
                 GOI_STAT_ADD(3, hit ? 1u : 0u);
 
-                // ---- per-pixel values (branch-free; rejected lanes publish zeros) ----
-                const float inv = rcp_approx(1.f - alpha);
-                const float Tn = T * inv;                   // reference: T = T / (1 - alpha)
-                const float wgt = alpha * Tn;
-                // q = payload . pixel-gradient + 1 * dL_dalpha, as four independent FMA chains (latency)
-                float q0 = fmaf(p0.x, g_rgb[0], g_alpha), q1 = p0.y * g_rgb[1], q2 = p0.z * g_rgb[2], q3 = p0.w * g_depth;
+                // ---- per-pixel values, branch-free.  A rejected lane is treated as a Gaussian of alpha 0 / G 0:
+                //      inv = 1, T unchanged, weight 0, and the (accn, last_q, last_alpha) recurrence stays exact
+                //      (the next step computes 0 * last_q + 1 * accn), so no per-value selects are needed.
+                const float a_eff = hit ? alpha : 0.f;
+                const float Gh = hit ? G : 0.f;
+                const float inv = rcp_approx(1.f - a_eff);
+                T = T * inv;                                // reference: T = T / (1 - alpha)
+                // q = payload . pixel-gradient + 1 * dL_dalpha: four independent chains in two FFMA2 streams
+                float2 qa = ffma2(make_float2(p0.x, p0.y), g01, make_float2(g_alpha, 0.f));
+                float2 qb = fmul2(make_float2(p0.z, p0.w), g2d);
 #pragma unroll
                 for (int k = 0; k < NS4; ++k) {
-                    q0 = fmaf(s4[k].x, g_sem[4 * k + 0], q0); q1 = fmaf(s4[k].y, g_sem[4 * k + 1], q1);
-                    q2 = fmaf(s4[k].z, g_sem[4 * k + 2], q2); q3 = fmaf(s4[k].w, g_sem[4 * k + 3], q3);
+                    qa = ffma2(make_float2(s4[k].x, s4[k].y), gs2[2 * k + 0], qa);
+                    qb = ffma2(make_float2(s4[k].z, s4[k].w), gs2[2 * k + 1], qb);
                 }
-                const float q = (q0 + q1) + (q2 + q3);
-                const float accn = last_alpha * last_q + (1.f - last_alpha) * acc;
-                float dL_dopa = (q - accn) * Tn;
-                dL_dopa += (-T_final * inv) * bg_dot_dpixel;
-                const float dL_dG = hit ? g1.y * dL_dopa : 0.f;
-                const float Gh = hit ? G : 0.f;             // rejected lanes must publish exact zeros (no 0*inf)
+                const float q = (qa.x + qa.y) + (qb.x + qb.y);
+                acc = fmaf(last_alpha, last_q, (1.f - last_alpha) * acc);
+                last_q = q;
+                last_alpha = a_eff;
+                // dL/dalpha = (q - acc) T - T_final bg.g / (1 - alpha)     (backward.cu:592-601)
+                const float dL_dopa = fmaf(nTf_bg, inv, (q - acc) * T);
+                const float dL_dG = g1.y * dL_dopa;
                 const float gdx = Gh * dx;
                 const float gdy = Gh * dy;
                 const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
                 const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-                const uint32_t ad = a_dyn + flip + lane * 4;
-                flip ^= DROWS * RSTRIDE * 4;
-                sts32(ad + 0 * RSTRIDE * 4, hit ? wgt : 0.f);
-                sts32(ad + 1 * RSTRIDE * 4, dL_dG * dG_ddelx * ddelx_dx);
-                sts32(ad + 2 * RSTRIDE * 4, dL_dG * dG_ddely * ddely_dy);
-                sts32(ad + 3 * RSTRIDE * 4, -0.5f * gdx * dx * dL_dG);
-                sts32(ad + 4 * RSTRIDE * 4, -0.5f * gdx * dy * dL_dG);
-                sts32(ad + 5 * RSTRIDE * 4, -0.5f * gdy * dy * dL_dG);
-                sts32(ad + 6 * RSTRIDE * 4, hit ? Gh * dL_dopa : 0.f);
-                // state update of contributing pixels
-                T = hit ? Tn : T;
-                acc = hit ? accn : acc;
-                last_q = hit ? q : last_q;
-                last_alpha = hit ? alpha : last_alpha;
+                const float hx = -0.5f * gdx * dL_dG, hy = -0.5f * gdy * dL_dG;
+                ad = ad_sum - ad;                           // other half of the double-buffered rows
+                sts32(ad + 0 * RSTRIDE * 4, a_eff * T);
+                sts32(ad + 1 * RSTRIDE * 4, dL_dG * dG_ddelx);
+                sts32(ad + 2 * RSTRIDE * 4, dL_dG * dG_ddely);
+                sts32(ad + 3 * RSTRIDE * 4, hx * dx);
+                sts32(ad + 4 * RSTRIDE * 4, hx * dy);
+                sts32(ad + 5 * RSTRIDE * 4, hy * dy);
+                sts32(ad + 6 * RSTRIDE * 4, Gh * dL_dopa);
                 __syncwarp();
 
                 // ---- reduction over the warp's 32 pixels: 4-pixel partial sums, then 8-lane butterfly ----
-                const uint32_t ar = ad - lane * 4 + pg * 16;                // this lane's 4 pixels in row 0
+                const uint32_t ar = ad + dl;                                // this lane's 4 pixels in row 0
                 const float4 w4 = lds128(ar);
-                const float4 e0 = lds128(ar + grow0 * RSTRIDE * 4);
-                const float4 e1 = lds128(ar + grow1 * RSTRIDE * 4);
+                const float4 e0 = lds128(ar + go);
+                const float4 e1 = lds128(ar + go + RSTRIDE * 4);
+                float vv[VPG];
+#pragma unroll
+                for (int u2 = 0; u2 < NP2; ++u2) {
+                    float2 t = fmul2(gp[u2][0], make_float2(w4.x, w4.x));
+                    t = ffma2(gp[u2][1], make_float2(w4.y, w4.y), t);
+                    t = ffma2(gp[u2][2], make_float2(w4.z, w4.z), t);
+                    t = ffma2(gp[u2][3], make_float2(w4.w, w4.w), t);
+                    vv[2 * u2] = t.x; vv[2 * u2 + 1] = t.y;
+                }
+                if (PPG & 1)
+                    vv[PPG - 1] = fmaf(w4.w, gtail[3], fmaf(w4.z, gtail[2], fmaf(w4.y, gtail[1], w4.x * gtail[0])));
+                {
+                    const float2 s0 = fadd2(make_float2(e0.x, e0.y), make_float2(e0.z, e0.w));
+                    const float2 s1 = fadd2(make_float2(e1.x, e1.y), make_float2(e1.z, e1.w));
+                    vv[PPG] = s0.x + s0.y;
+                    vv[PPG + 1] = s1.x + s1.y;
+                }
+                // second stage: transpose through shared memory -- value u of this lane's pixel group goes to
+                // [vg][u][pg]; the lane that owns output u = 8k + pg then reads the 8 pixel-group partials of that
+                // value as two LDS.128 (18 instructions where a shuffle butterfly needs ~36)
+#pragma unroll
+                for (int u = 0; u < VPG; ++u) sts32(atw + u * (USTRIDE * 4), vv[u]);
+                __syncwarp();
 #pragma unroll
                 for (int k = 0; k < NBLK; ++k) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int u = 8 * k + i;                                 // compile-time
-                        if (u < PPG) {
-                            const int uu = u < PPG ? u : 0;
-                            v[i] = fmaf(w4.w, gsel[uu][3], fmaf(w4.z, gsel[uu][2], fmaf(w4.y, gsel[uu][1], w4.x * gsel[uu][0])));
-                        } else if (u == PPG) v[i] = gsc0 * ((e0.x + e0.y) + (e0.z + e0.w));
-                        else if (u == PPG + 1) v[i] = gsc1 * ((e1.x + e1.y) + (e1.z + e1.w));
-                        else v[i] = 0.f;
-                    }
-                    const float r = group8_transpose_reduce(v, lane);
-                    if (out_ptr[k]) atomicAdd(out_ptr[k] + (uint32_t)id * out_stride[k], r);
+                    const float4 a = lds128(atr + k * (8 * USTRIDE * 4));
+                    const float4 c = lds128(atr + k * (8 * USTRIDE * 4) + 16);
+                    const float r = (((a.x + a.y) + (a.z + a.w)) + ((c.x + c.y) + (c.z + c.w))) * out_scale[k];
+                    if (out_stride[k]) atomicAdd(out_ptr[k] + (uint32_t)id * out_stride[k], r);
                 }
             }
         }
@@ -341,7 +369,9 @@ static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const
     constexpr int BATCH = 128;
     constexpr int ROW = 1 + NS4;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
-    const size_t smem = (size_t)2 * BATCH * (2 + ROW) * sizeof(float4) + (size_t)(8 * 2 * 7) * RSTRIDE * sizeof(float);
+    constexpr int NBLK = ((4 + 4 * NS4 + 3) / 4 + 2 + 7) / 8;
+    const size_t smem = (size_t)2 * BATCH * (2 + ROW) * sizeof(float4) + (size_t)(8 * 2 * 7) * RSTRIDE * sizeof(float) +
+                        (size_t)8 * 4 * (NBLK * 8 * 12 + 8) * sizeof(float);
     auto kern = k_composite_bwd<NS4, BATCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

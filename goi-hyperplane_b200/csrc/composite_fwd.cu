@@ -45,7 +45,6 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     float4* s_g0 = smem;                               // [2][BATCH] (mean.x, mean.y, conic.x, conic.y)
     float4* s_g1 = smem + 2 * BATCH;                   // [2][BATCH] (conic.z, opacity, power_cut, -)
     float4* s_pay = smem + 4 * BATCH;                  // [2][BATCH][ROW]
-    __shared__ int s_id[2][BATCH];                     // Gaussian ids (trace mode scatters by id)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -82,7 +81,6 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 cp_async16(&s_g0[buf * BATCH + j], &geo[2 * (size_t)id]);
                 cp_async16(&s_g1[buf * BATCH + j], &geo[2 * (size_t)id + 1]);
                 cp_async16(&s_pay[(buf * BATCH + j) * ROW], &rgbd[id]);
-                if (TRACE) s_id[buf][j] = (int)id;
             } else {
                 float4* dst = &s_pay[(buf * BATCH + j) * ROW + 1];
                 const float* src = sem + (size_t)id * S;
@@ -98,10 +96,11 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
-    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dacc = 0.f;
-    float Cs[NS4 > 0 ? 4 * NS4 : 1];
+    // accumulators as register pairs for FFMA2: (r,g) (b,depth) and 2*NS4 semantic pairs
+    float2 C01 = make_float2(0.f, 0.f), C2D = make_float2(0.f, 0.f);
+    float2 Cs[NS4 > 0 ? 2 * NS4 : 1];
 #pragma unroll
-    for (int i = 0; i < (NS4 > 0 ? 4 * NS4 : 1); ++i) Cs[i] = 0.f;
+    for (int i = 0; i < (NS4 > 0 ? 2 * NS4 : 1); ++i) Cs[i] = make_float2(0.f, 0.f);
     int done = inside ? 0 : 1;                          // int, not bool: keeps the loop free of byte packing
     bool warp_done = __all_sync(0xffffffffu, done);
     const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
@@ -150,20 +149,19 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                     const float w = hit ? alpha * T : 0.f;
                     const uint32_t ap = apay + j * (ROW * 16);
                     const float4 p0 = lds128(ap);
-                    C0 = fmaf(p0.x, w, C0); C1 = fmaf(p0.y, w, C1); C2 = fmaf(p0.z, w, C2);
+                    const float2 ww = make_float2(w, w);
+                    C01 = ffma2(make_float2(p0.x, p0.y), ww, C01);
+                    C2D = ffma2(make_float2(p0.z, p0.w), ww, C2D);      // depth lane unused by trace
                     if (!TRACE) {
-                        Dacc = fmaf(p0.w, w, Dacc);
 #pragma unroll
                         for (int k = 0; k < NS4; ++k) {
                             const float4 s4 = lds128(ap + 16 + 16 * k);
-                            Cs[4 * k + 0] = fmaf(s4.x, w, Cs[4 * k + 0]);
-                            Cs[4 * k + 1] = fmaf(s4.y, w, Cs[4 * k + 1]);
-                            Cs[4 * k + 2] = fmaf(s4.z, w, Cs[4 * k + 2]);
-                            Cs[4 * k + 3] = fmaf(s4.w, w, Cs[4 * k + 3]);
+                            Cs[2 * k + 0] = ffma2(make_float2(s4.x, s4.y), ww, Cs[2 * k + 0]);
+                            Cs[2 * k + 1] = ffma2(make_float2(s4.z, s4.w), ww, Cs[2 * k + 1]);
                         }
                     } else if (hit && alpha > 0.005) {
                         // traceCUDA, forward.cu:521-526, with atomics instead of the reference's racy `+=`
-                        const int id = s_id[buf][j];
+                        const int id = __float_as_int(g1.w);       // index bits stored by preprocess
                         for (int ch = 0; ch < S; ++ch) atomicAdd(&gau_sem[(size_t)id * S + ch], img_sem[ch * HW + pix]);
                         atomicAdd(&num_gsem[id], count_per_channel ? S : 1);
                     }
@@ -178,15 +176,15 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     GOI_STAT_FLUSH(0);
     if (inside) {
         n_contrib[pix] = last_contributor;
-        out_color[pix] = C0 + T * bg[0];
-        out_color[HW + pix] = C1 + T * bg[1];
-        out_color[2 * HW + pix] = C2 + T * bg[2];
+        out_color[pix] = C01.x + T * bg[0];
+        out_color[HW + pix] = C01.y + T * bg[1];
+        out_color[2 * HW + pix] = C2D.x + T * bg[2];
         if (!TRACE) {
 #pragma unroll
             for (int ch = 0; ch < 4 * NS4; ++ch)
-                if (ch < S) out_sem[ch * HW + pix] = Cs[ch];
+                if (ch < S) out_sem[ch * HW + pix] = (ch & 1) ? Cs[ch >> 1].y : Cs[ch >> 1].x;
             out_alpha[pix] = 1 - T;
-            out_depth[pix] = Dacc;
+            out_depth[pix] = C2D.y;
         }
     }
 }

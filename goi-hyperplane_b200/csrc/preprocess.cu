@@ -15,7 +15,8 @@
 //
 // Layout written for the composite kernels (HBM, private to this library, see goi_internal.cuh):
 //   geo[2i]   = (mean2D.x, mean2D.y, conic.x, conic.y)        32 B per Gaussian, two float4 so one
-//   geo[2i+1] = (conic.z, opacity, power_cut, 0)              instance costs 2 x 16 B cp.async
+//   geo[2i+1] = (conic.z, opacity, power_cut, bits(i))        instance costs 2 x 16 B cp.async; the index
+//                                                             rides along so the walk needs no id array
 //   rgbd[i]   = (r, g, b, depth)
 #include "goi_internal.cuh"
 #include "goi_cull.cuh"
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
 
     radii[idx] = max_radius;
     geo[2 * idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-    geo[2 * idx + 1] = make_float4(conic.z, opacity, power_cut, 0.f);
+    geo[2 * idx + 1] = make_float4(conic.z, opacity, power_cut, __int_as_float(idx));
     rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, depth);
     rect[idx] = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
     // Instances = tiles of the reference rectangle that can actually reach alpha >= 1/255 (goi_cull.cuh).
