@@ -294,7 +294,7 @@ int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_f
     int selector = 0;
     GOI_CUDA(run_binning(*view, g->P, out->radii, gs, bs, is, num_rendered, &selector, st), "binning");
     if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
-    { StageScope sc(ST_COMPOSITE_FWD, st); GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], is, st), "composite forward"); }
+    { StageScope sc(ST_COMPOSITE_FWD, st); GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], is, st), "composite forward"); }
     return debug_sync(view, st, "composite forward");
 }
 
@@ -377,7 +377,7 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
 
     if (num_rendered > 0) {
         StageScope sc(ST_COMPOSITE_BWD, st);
-        GOI_CUDA(launch_composite_bwd(*view, *g, *in, o2, gs, bs.vals[0], is, st), "composite backward");
+        GOI_CUDA(launch_composite_bwd(*view, *g, *in, o2, gs, bs.vals[0], bs.vals[1], is, st), "composite backward");
     }
     if ((rc = debug_sync(view, st, "composite backward")) != GOI_OK) return rc;
     { StageScope sc(ST_PREPROCESS_BWD, st); GOI_CUDA(launch_preprocess_bwd(*view, *g, *in, *out, gs, st), "preprocess backward"); }

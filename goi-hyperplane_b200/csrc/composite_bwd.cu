@@ -43,7 +43,8 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp: x =
 
 template <int NS4, int BATCH>
 __global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 3 : 1))
-k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                const uint32_t* __restrict__ cull, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg, const float* __restrict__ out_alpha,
                 const uint32_t* __restrict__ n_contrib,
@@ -71,6 +72,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     constexpr int VS = NBLK * 8 * USTRIDE + 8;         // floats per value group: (VS mod 32 == 8) keeps the STS conflict-free
     float* s_tr = s_red + 8 * 2 * DROWS * RSTRIDE;
     __shared__ uint32_t s_max_contrib;
+    __shared__ uint32_t s_cull[2][BATCH];              // the forward's warp-block masks of the staged instances
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pg = lane & 7, vg = lane >> 3;
@@ -83,8 +85,6 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     const float pxf = (float)px, pyf = (float)py;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
-    const float rx0 = (float)wx0, rx1 = (float)min(wx0 + 7, W - 1);
-    const float ry0 = (float)wy0, ry1 = (float)min(wy0 + 3, H - 1);
     const uint2 range = ranges[tile];
 
     if (tid == 0) s_max_contrib = 0;
@@ -165,8 +165,10 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         constexpr int PARTS = NS4 > 0 ? 2 : 1;
         for (int wi = tid; wi < cnt * PARTS; wi += COMPOSITE_THREADS) {
             const int j = wi / PARTS, part = wi % PARTS;
-            const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - b * BATCH - j)];
+            const uint32_t li = range.x + (uint32_t)(n - 1 - b * BATCH - j);
+            const uint32_t id = point_list[li];
             if (part == 0) {
+                cp_async4(&s_cull[buf][j], &cull[li]);
                 cp_async16(&s_g0[buf * BATCH + j], &geo[2 * (size_t)id]);
                 cp_async16(&s_g1[buf * BATCH + j], &geo[2 * (size_t)id + 1]);
                 cp_async16(&s_pay[(buf * BATCH + j) * ROW], &rgbd[id]);
@@ -250,13 +252,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         const uint32_t apay = a_pay + buf * BATCH * ROW * 16;
         const int first_idx = n - 1 - b * BATCH;        // list index of j = 0
         for (int c0 = 0; c0 < cnt; c0 += 32) {
-            bool keep = false;
-            if (c0 + lane < cnt) {
-                const float4 a = lds128(ag0 + (c0 + lane) * 16);
-                const float4 q = lds128(ag1 + (c0 + lane) * 16);
-                keep = rect_may_contribute(a.x, a.y, a.z, a.w, q.x, q.z, rx0, rx1, ry0, ry1);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, keep);
+            unsigned m = __ballot_sync(0xffffffffu, (c0 + lane < cnt) && ((s_cull[buf][c0 + lane] >> warp) & 1u));
             GOI_STAT_ADD(0, (c0 + lane < cnt) ? 1u : 0u);
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
@@ -364,7 +360,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 template <int NS4>
 static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                 const goi_bwd_out& out, const GeomState& gs, const uint32_t* point_list,
-                                const ImageState& is, cudaStream_t st)
+                                const uint32_t* cull, const ImageState& is, cudaStream_t st)
 {
     constexpr int BATCH = 128;
     constexpr int ROW = 1 + NS4;
@@ -377,7 +373,7 @@ static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const
     if (e != cudaSuccess) return e;
     const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
     kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(
-        is.ranges, point_list, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S, sem_vec, v.background,
+        is.ranges, point_list, cull, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S, sem_vec, v.background,
         in.out_alpha, is.n_contrib, in.dL_dcolor, in.dL_dsemantic, in.dL_ddepth, in.dL_dalpha,
         out.dL_dmean2D, out.dL_dconic, out.dL_dopacity, out.dL_dcolor, out.dL_dsemantic, out.dL_ddepth);
     count_launches(1);
@@ -386,16 +382,16 @@ static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const
 
 cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                  const goi_bwd_out& out, const GeomState& gs, const uint32_t* point_list,
-                                 const ImageState& is, cudaStream_t st)
+                                 const uint32_t* cull, const ImageState& is, cudaStream_t st)
 {
     switch (sem_groups(g.S)) {
-        case 0: return launch_bwd_t<0>(v, g, in, out, gs, point_list, is, st);
-        case 1: return launch_bwd_t<1>(v, g, in, out, gs, point_list, is, st);
-        case 2: return launch_bwd_t<2>(v, g, in, out, gs, point_list, is, st);
-        case 3: return launch_bwd_t<3>(v, g, in, out, gs, point_list, is, st);
-        case 4: return launch_bwd_t<4>(v, g, in, out, gs, point_list, is, st);
-        case 8: return launch_bwd_t<8>(v, g, in, out, gs, point_list, is, st);
-        default: return launch_bwd_t<16>(v, g, in, out, gs, point_list, is, st);
+        case 0: return launch_bwd_t<0>(v, g, in, out, gs, point_list, cull, is, st);
+        case 1: return launch_bwd_t<1>(v, g, in, out, gs, point_list, cull, is, st);
+        case 2: return launch_bwd_t<2>(v, g, in, out, gs, point_list, cull, is, st);
+        case 3: return launch_bwd_t<3>(v, g, in, out, gs, point_list, cull, is, st);
+        case 4: return launch_bwd_t<4>(v, g, in, out, gs, point_list, cull, is, st);
+        case 8: return launch_bwd_t<8>(v, g, in, out, gs, point_list, cull, is, st);
+        default: return launch_bwd_t<16>(v, g, in, out, gs, point_list, cull, is, st);
     }
 }
 

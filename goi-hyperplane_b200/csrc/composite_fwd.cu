@@ -36,15 +36,18 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 int S, int sem_vec, const float* __restrict__ bg,
                 float* __restrict__ out_color, float* __restrict__ out_sem, float* __restrict__ out_depth,
                 float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
+                uint32_t* __restrict__ cull_out,       // [R] per list entry: bit w = warp block w may contribute
                 // trace mode only:
                 const float* __restrict__ img_sem, float* __restrict__ gau_sem, int32_t* __restrict__ num_gsem,
                 int count_per_channel)
 {
     constexpr int ROW = 1 + NS4;                       // float4 per payload row: (r,g,b,depth) + semantics
     extern __shared__ float4 smem[];
-    float4* s_g0 = smem;                               // [2][BATCH] (mean.x, mean.y, conic.x, conic.y)
-    float4* s_g1 = smem + 2 * BATCH;                   // [2][BATCH] (conic.z, opacity, power_cut, -)
-    float4* s_pay = smem + 4 * BATCH;                  // [2][BATCH][ROW]
+    constexpr int NST = 3;                             // staging depth: batch b is walked while b+1 is culled and b+2 lands
+    float4* s_g0 = smem;                               // [NST][BATCH] (mean.x, mean.y, conic.x, conic.y)
+    float4* s_g1 = smem + NST * BATCH;                 // [NST][BATCH] (conic.z, opacity, power_cut, index bits)
+    float4* s_pay = smem + 2 * NST * BATCH;            // [NST][BATCH][ROW]
+    __shared__ uint32_t s_cull[2][BATCH];              // per staged instance: 8-bit warp-block mask
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -56,21 +59,25 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     const float pxf = (float)px, pyf = (float)py;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
-    // pixel-centre rectangle of this warp, clipped to the image
-    const float rx0 = (float)wx0, rx1 = (float)min(wx0 + 7, W - 1);
-    const float ry0 = (float)wy0, ry1 = (float)min(wy0 + 3, H - 1);
-
+    // Cooperative cull, one batch ahead of the walk: thread t tests staged instance t >> 1 against the four 8x4
+    // warp blocks of tile rows 8 (t & 1) .. 8 (t & 1) + 7 (pixel-centre rectangles clipped to the image), so the
+    // two reciprocals of the bound are paid once per instance instead of once per (warp, instance).  The 8-bit
+    // mask is published in shared memory for the walk and in global memory for the backward.
+    const int cj = tid >> 1, ch = tid & 1;
+    const float cx0 = (float)(tx * TILE), cx1 = (float)min(tx * TILE + 7, W - 1);
+    const float cx2 = (float)(tx * TILE + 8), cx3 = (float)min(tx * TILE + 15, W - 1);
+    const int cy = ty * TILE + 8 * ch;
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
     const int nb = (n + BATCH - 1) / BATCH;
 
     if (!TRACE && NS4 > 0 && 4 * NS4 != S) {           // padded semantic lanes must read as zero
-        for (int i = tid; i < 2 * BATCH * ROW; i += COMPOSITE_THREADS) s_pay[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < NST * BATCH * ROW; i += COMPOSITE_THREADS) s_pay[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
     }
 
     auto stage = [&](int b) {
-        const int buf = b & 1;
+        const int buf = b % NST;
         const int base = (int)range.x + b * BATCH;
         const int cnt = min(BATCH, n - b * BATCH);
         constexpr int PARTS = (!TRACE && NS4 > 0) ? 2 : 1;
@@ -106,27 +113,52 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
     GOI_STAT_DECL;
 
-    if (nb > 0) stage(0);
-    for (int b = 0; b < nb; ++b) {
-        cp_async_wait_all();
-        if (__syncthreads_count(!done) == 0) break;     // batch b landed; batch b-1 fully consumed
-        if (b + 1 < nb) stage(b + 1);
-        if (warp_done) continue;
+    auto cull_batch = [&](int b) {                      // batch b has landed and is visible to the whole CTA
+        const int buf = b % NST, cnt = min(BATCH, n - b * BATCH);
+        uint32_t m = 0;
+        if (cj < cnt) {
+            const float4 a = s_g0[buf * BATCH + cj];
+            const float4 q = s_g1[buf * BATCH + cj];
+            CullGaussian cg;
+            cg.set(a.x, a.y, a.z, a.w, q.x, q.z);
+            const float y0 = (float)cy, y1 = (float)min(cy + 3, H - 1), y2 = (float)(cy + 4), y3 = (float)min(cy + 7, H - 1);
+            m = (cg.may_contribute(cx0, cx1, y0, y1) ? 1u : 0u) | (cg.may_contribute(cx2, cx3, y0, y1) ? 2u : 0u) |
+                (cg.may_contribute(cx0, cx1, y2, y3) ? 4u : 0u) | (cg.may_contribute(cx2, cx3, y2, y3) ? 8u : 0u);
+            m <<= 4 * ch;
+        }
+        m |= __shfl_xor_sync(0xffffffffu, m, 1);
+        if (ch == 0) {
+            s_cull[b & 1][cj] = m;                      // rows past cnt are zero
+            if (cull_out && cj < cnt) cull_out[range.x + (uint32_t)(b * BATCH + cj)] = m;
+        }
+    };
 
-        const int buf = b & 1;
+    if (nb > 0) {
+        stage(0);
+        if (nb > 1) stage(1);
+        cp_async_wait_all();
+        __syncthreads();
+        cull_batch(0);
+    }
+    for (int b = 0; b < nb; ++b) {
+        // one barrier per batch: batches b and b+1 have landed, the masks of batch b are visible, and the
+        // stage of batch b-1 (reused by b+2) is fully consumed
+        cp_async_wait_all();
+        if (__syncthreads_count(!done) == 0) break;
+        if (b + 2 < nb) stage(b + 2);
+        if (b + 1 < nb) cull_batch(b + 1);
+
+        const int buf = b % NST;
         const int cnt = min(BATCH, n - b * BATCH);
         const uint32_t ag0 = a_g0 + buf * BATCH * 16, ag1 = a_g1 + buf * BATCH * 16;
+        if (warp_done) continue;
+
         const uint32_t apay = a_pay + buf * BATCH * ROW * 16;
         const uint32_t list_base = (uint32_t)(b * BATCH + 1);
         for (int c0 = 0; c0 < cnt && !warp_done; c0 += 32) {
             // lanes test 32 instances in parallel against this warp's pixel rectangle
-            bool keep = false;
-            if (c0 + lane < cnt) {
-                const float4 a = lds128(ag0 + (c0 + lane) * 16);
-                const float4 q = lds128(ag1 + (c0 + lane) * 16);
-                keep = rect_may_contribute(a.x, a.y, a.z, a.w, q.x, q.z, rx0, rx1, ry0, ry1);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, keep);
+            // s_cull rows past cnt are zero
+            unsigned m = __ballot_sync(0xffffffffu, (s_cull[b & 1][c0 + lane] >> warp) & 1u);
             GOI_STAT_ADD(0, (c0 + lane < cnt) ? 1u : 0u);
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
@@ -191,31 +223,31 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 
 template <int NS4, bool TRACE>
 static cudaError_t launch_fwd_t(const goi_view& v, const goi_gaussians& g, const GeomState& gs,
-                                const uint32_t* point_list, const ImageState& is, float* out_color,
+                                const uint32_t* point_list, uint32_t* cull_out, const ImageState& is, float* out_color,
                                 float* out_sem, float* out_depth, float* out_alpha, const float* img_sem,
                                 float* gau_sem, int32_t* num_gsem, int count_per_channel, cudaStream_t st)
 {
     constexpr int BATCH = 128;
     constexpr int ROW = 1 + NS4;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
-    const size_t smem = (size_t)2 * BATCH * (2 + ROW) * sizeof(float4);
+    const size_t smem = (size_t)3 * BATCH * (2 + ROW) * sizeof(float4);
     auto kern = k_composite_fwd<NS4, BATCH, TRACE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
     kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(is.ranges, point_list, v.width, v.height, gx, gs.geo, gs.rgbd,
                                                    g.semantics, g.S, sem_vec, v.background, out_color, out_sem,
-                                                   out_depth, out_alpha, is.n_contrib, img_sem, gau_sem, num_gsem,
-                                                   count_per_channel);
+                                                   out_depth, out_alpha, is.n_contrib, cull_out, img_sem, gau_sem,
+                                                   num_gsem, count_per_channel);
     count_launches(1);
     return cudaGetLastError();
 }
 
 cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
-                                 const GeomState& gs, const uint32_t* point_list, const ImageState& is,
-                                 cudaStream_t st)
+                                 const GeomState& gs, const uint32_t* point_list, uint32_t* cull_out,
+                                 const ImageState& is, cudaStream_t st)
 {
-#define GOI_FWD(N) return launch_fwd_t<N, false>(v, g, gs, point_list, is, out.out_color, out.out_semantic, \
+#define GOI_FWD(N) return launch_fwd_t<N, false>(v, g, gs, point_list, cull_out, is, out.out_color, out.out_semantic, \
                                                   out.out_depth, out.out_alpha, nullptr, nullptr, nullptr, 0, st)
     switch (sem_groups(g.S)) {
         case 0: GOI_FWD(0);
@@ -233,7 +265,7 @@ cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float*
                          float* gau_sem, int32_t* num_gsem, int count_per_channel, const GeomState& gs,
                          const uint32_t* point_list, const ImageState& is, cudaStream_t st)
 {
-    return launch_fwd_t<0, true>(v, g, gs, point_list, is, out_color, nullptr, nullptr, nullptr, img_sem, gau_sem,
+    return launch_fwd_t<0, true>(v, g, gs, point_list, nullptr, is, out_color, nullptr, nullptr, nullptr, img_sem, gau_sem,
                                  num_gsem, count_per_channel, st);
 }
 

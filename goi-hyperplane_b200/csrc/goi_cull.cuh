@@ -54,6 +54,34 @@ __device__ __forceinline__ bool rect_may_contribute(float mx, float my, float A,
     return !(rect_max_power(mx, my, A, B, C, x0, x1, y0, y1) < __fsub_rn(power_cut, kCullSlack));
 }
 
+// Same bound with the two reciprocals hoisted: one Gaussian tested against several rectangles (the 8x4 warp
+// blocks of a tile) pays for the divisions once.  Conservative like rect_max_power; it does not have to agree
+// bit for bit with anything (only the tile-level test is evaluated twice).
+struct CullGaussian {
+    float mx, my, A, B, C, nb_c, nb_a, cut;
+    // (the maximiser only needs ~1 ulp: MUFU.RCP; a misplaced maximiser changes the bound to second order)
+    __device__ __forceinline__ void set(float mx_, float my_, float A_, float B_, float C_, float power_cut)
+    {
+        mx = mx_; my = my_; A = A_; B = B_; C = C_;
+        nb_c = -B_ * __frcp_rn(C_); nb_a = -B_ * __frcp_rn(A_);
+        cut = power_cut - kCullSlack;
+    }
+    __device__ __forceinline__ bool may_contribute(float x0, float x1, float y0, float y1) const
+    {
+        const float dx0 = mx - x1, dx1 = mx - x0, dy0 = my - y1, dy1 = my - y0;
+        if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return true;
+        float dy = fminf(fmaxf(nb_c * dx0, dy0), dy1);
+        float best = pair_power(A, B, C, dx0, dy);
+        dy = fminf(fmaxf(nb_c * dx1, dy0), dy1);
+        best = fmaxf(best, pair_power(A, B, C, dx1, dy));
+        float dx = fminf(fmaxf(nb_a * dy0, dx0), dx1);
+        best = fmaxf(best, pair_power(A, B, C, dx, dy0));
+        dx = fminf(fmaxf(nb_a * dy1, dx0), dx1);
+        best = fmaxf(best, pair_power(A, B, C, dx, dy1));
+        return !(best < cut);
+    }
+};
+
 // Tile (tx,ty) of a W x H image.
 __device__ __forceinline__ bool tile_may_contribute(float mx, float my, float A, float B, float C, float power_cut,
                                                     int tx, int ty, int W, int H)

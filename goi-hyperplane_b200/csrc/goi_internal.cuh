@@ -50,7 +50,7 @@ struct ImageState {
 };
 struct BinningState {
     uint32_t* keys[2];           // double buffer: tile id (instances are emitted in depth order)
-    uint32_t* vals[2];           // double buffer: Gaussian index
+    uint32_t* vals[2];           // double buffer: Gaussian index; after the sort [0] = list, [1] = cull masks
     uint32_t* selector;          // (device) unused; host keeps the selector in the header word below
     char*     sort_temp;
     size_t    sort_temp_bytes;
@@ -94,12 +94,14 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
 size_t scan_temp_bytes_for(int P);
 size_t sort_temp_bytes_for(int64_t R);
 
+// cull: per list entry, bit w set = the 8x4 pixel block of warp w may blend this instance (written by the
+// forward composite into the dead half of the sort's value double buffer, read back by the backward)
 cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
-                                 const GeomState& gs, const uint32_t* point_list, const ImageState& is,
-                                 cudaStream_t st);
+                                 const GeomState& gs, const uint32_t* point_list, uint32_t* cull_out,
+                                 const ImageState& is, cudaStream_t st);
 cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                  const goi_bwd_out& out, const GeomState& gs, const uint32_t* point_list,
-                                 const ImageState& is, cudaStream_t st);
+                                 const uint32_t* cull, const ImageState& is, cudaStream_t st);
 cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                   const goi_bwd_out& out, const GeomState& gs, cudaStream_t st);
 cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float* img_sem, float* out_color,
