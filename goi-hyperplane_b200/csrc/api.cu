@@ -264,20 +264,48 @@ int goi_forward_prepare(const goi_view* view, const goi_gaussians* g, int32_t* r
     return GOI_OK;
 }
 
-int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, void* geom_buf,
-                       size_t geom_bytes, void* binning_buf, size_t binning_bytes, void* image_buf,
-                       size_t image_bytes, int64_t num_rendered, void* stream)
+static int validate_mask(const goi_mask_args* a, bool standalone)
+{
+    if (!a) return fail(GOI_ERR_INVALID_ARG, "null args");
+    if (a->N < 0 || a->S <= 0 || a->K <= 0 || a->D <= 0) return fail(GOI_ERR_INVALID_ARG, "bad N/S/K/D");
+    if (a->S > GOI_MAX_SEM) return fail(GOI_ERR_UNSUPPORTED, "S=%d > GOI_MAX_SEM", a->S);
+    if (a->mode != GOI_MASK_APE && a->mode != GOI_MASK_OSH) return fail(GOI_ERR_INVALID_ARG, "bad mode");
+    if ((standalone && !a->x) || !a->mlp_weight || !a->lut || !a->hyperplane_w || !a->sim_table || !a->sim)
+        return fail(GOI_ERR_INVALID_ARG, "null pointers");
+    const size_t smem = (size_t)a->K * sem_groups(a->S) * 16 + 2 * (size_t)a->K * 4;
+    if (smem > 200 * 1024) return fail(GOI_ERR_UNSUPPORTED, "codebook projection (K=%d, S=%d) does not fit shared memory", a->K, a->S);
+    return GOI_OK;
+}
+
+// mask == NULL: plain forward.  mask != NULL: the composite also evaluates the hyperplane mask per pixel in
+// its epilogue (out->out_semantic may then be NULL = the semantic image is not wanted).
+static int forward_render_impl(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
+                               const goi_mask_args* mask, void* geom_buf, size_t geom_bytes, void* binning_buf,
+                               size_t binning_bytes, void* image_buf, size_t image_bytes, int64_t num_rendered,
+                               void* stream)
 {
     int rc = validate(view, g);
     if (rc != GOI_OK) return rc;
-    if (!out || !out->out_color || !out->out_depth || !out->out_alpha || (g->S > 0 && !out->out_semantic))
+    if (!out || !out->out_color || !out->out_depth || !out->out_alpha || (g->S > 0 && !out->out_semantic && !mask))
         return fail(GOI_ERR_INVALID_ARG, "output image pointers are NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if (mask) {
+        if ((rc = validate_mask(mask, false)) != GOI_OK) return rc;
+        if (mask->S != g->S) return fail(GOI_ERR_INVALID_ARG, "mask S=%d != semantic channels S=%d", mask->S, g->S);
+        if (mask->N != (int64_t)view->width * view->height) return fail(GOI_ERR_INVALID_ARG, "mask N != width*height");
+        GOI_CUDA(launch_mask_table(*mask, st), "mask table");
+    }
+    if (g->P == 0 && mask) {
+        // nothing rendered: every pixel's semantic vector is 0, so the logits are the biases
+        const size_t HW = (size_t)view->width * view->height;
+        if (out->out_semantic) GOI_CUDA(cudaMemsetAsync(out->out_semantic, 0, sizeof(float) * g->S * HW, st), "empty");
+        GOI_CUDA(launch_mask_zero_input(*mask, st), "mask");
+    }
     if (g->P == 0) {
         // reference: nothing is rendered, outputs keep their zero fill (rasterize_points.cu:69-85)
         const size_t HW = (size_t)view->width * view->height;
         GOI_CUDA(cudaMemsetAsync(out->out_color, 0, sizeof(float) * 3 * HW, st), "empty");
-        if (g->S > 0) GOI_CUDA(cudaMemsetAsync(out->out_semantic, 0, sizeof(float) * g->S * HW, st), "empty");
+        if (g->S > 0 && out->out_semantic) GOI_CUDA(cudaMemsetAsync(out->out_semantic, 0, sizeof(float) * g->S * HW, st), "empty");
         GOI_CUDA(cudaMemsetAsync(out->out_depth, 0, sizeof(float) * HW, st), "empty");
         GOI_CUDA(cudaMemsetAsync(out->out_alpha, 0, sizeof(float) * HW, st), "empty");
         return GOI_OK;
@@ -294,8 +322,34 @@ int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_f
     int selector = 0;
     GOI_CUDA(run_binning(*view, g->P, out->radii, gs, bs, is, num_rendered, &selector, st), "binning");
     if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
-    { StageScope sc(ST_COMPOSITE_FWD, st); GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], is, st), "composite forward"); }
+    {
+        StageScope sc(ST_COMPOSITE_FWD, st);
+        if (mask) GOI_CUDA(launch_composite_fwd_mask(*view, *g, *out, *mask, gs, bs.vals[0], bs.vals[1], is, st), "composite forward + mask");
+        else GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], is, st), "composite forward");
+    }
     return debug_sync(view, st, "composite forward");
+}
+
+int goi_forward_render(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, void* geom_buf,
+                       size_t geom_bytes, void* binning_buf, size_t binning_bytes, void* image_buf,
+                       size_t image_bytes, int64_t num_rendered, void* stream)
+{
+    return forward_render_impl(view, g, out, nullptr, geom_buf, geom_bytes, binning_buf, binning_bytes, image_buf,
+                               image_bytes, num_rendered, stream);
+}
+
+int goi_forward_mask(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, const goi_mask_args* mask,
+                     void* geom_buf, size_t geom_bytes, void* binning_buf, size_t binning_bytes, void* image_buf,
+                     size_t image_bytes, void* stream, int64_t* num_rendered)
+{
+    if (!out || !mask) return fail(GOI_ERR_INVALID_ARG, "out/mask is NULL");
+    if (!g || g->S <= 0) return fail(GOI_ERR_INVALID_ARG, "the fused mask needs semantic channels (S > 0)");
+    int rc = goi_forward_prepare(view, g, out->radii, geom_buf, geom_bytes, stream, num_rendered);
+    if (rc != GOI_OK) return rc;
+    if (binning_bytes < goi_binning_bytes(*num_rendered))
+        return fail(GOI_ERR_WORKSPACE, "binning buffer too small for %lld instances", (long long)*num_rendered);
+    return forward_render_impl(view, g, out, mask, geom_buf, geom_bytes, binning_buf, binning_bytes, image_buf,
+                               image_bytes, *num_rendered, stream);
 }
 
 int goi_forward_auto(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, void* geom_buf,
@@ -435,14 +489,8 @@ int goi_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, c
 
 int goi_mask(const goi_mask_args* a, void* stream)
 {
-    if (!a) return fail(GOI_ERR_INVALID_ARG, "null args");
-    if (a->N < 0 || a->S <= 0 || a->K <= 0 || a->D <= 0) return fail(GOI_ERR_INVALID_ARG, "bad N/S/K/D");
-    if (a->S > GOI_MAX_SEM) return fail(GOI_ERR_UNSUPPORTED, "S=%d > GOI_MAX_SEM", a->S);
-    if (a->mode != GOI_MASK_APE && a->mode != GOI_MASK_OSH) return fail(GOI_ERR_INVALID_ARG, "bad mode");
-    if (!a->x || !a->mlp_weight || !a->lut || !a->hyperplane_w || !a->sim_table || !a->sim)
-        return fail(GOI_ERR_INVALID_ARG, "null pointers");
-    const size_t smem = (size_t)a->K * sem_groups(a->S) * 16 + 2 * (size_t)a->K * 4;
-    if (smem > 200 * 1024) return fail(GOI_ERR_UNSUPPORTED, "codebook projection (K=%d, S=%d) does not fit shared memory", a->K, a->S);
+    const int rc = validate_mask(a, true);
+    if (rc != GOI_OK) return rc;
     GOI_CUDA(launch_mask(*a, (cudaStream_t)stream), "mask");
     return GOI_OK;
 }

@@ -29,7 +29,20 @@
 
 namespace goi {
 
-template <int NS4, int BATCH, bool TRACE>
+// Fused mask epilogue: the codebook projection + arg-max + sim-table lookup of
+// mask.cu applied to the pixel's semantic accumulators while they are still in registers.
+struct MaskEpilogue {
+    const float* mlp_w;        // [K,S]
+    const float* mlp_b;        // [K] or NULL
+    const float* sim_table;    // [K]   (k_mask_table)
+    int K;
+    float thresh;
+    float* sim;                // [H*W]
+    uint8_t* bg_mask;          // [H*W] or NULL
+    int32_t* idx;              // [H*W] or NULL
+};
+
+template <int NS4, int BATCH, bool TRACE, bool MASK>
 __global__ void __launch_bounds__(COMPOSITE_THREADS)
 k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
@@ -39,7 +52,7 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 uint32_t* __restrict__ cull_out,       // [R] per list entry: bit w = warp block w may contribute
                 // trace mode only:
                 const float* __restrict__ img_sem, float* __restrict__ gau_sem, int32_t* __restrict__ num_gsem,
-                int count_per_channel)
+                int count_per_channel, MaskEpilogue me)
 {
     constexpr int ROW = 1 + NS4;                       // float4 per payload row: (r,g,b,depth) + semantics
     extern __shared__ float4 smem[];
@@ -212,33 +225,76 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         out_color[HW + pix] = C01.y + T * bg[1];
         out_color[2 * HW + pix] = C2D.x + T * bg[2];
         if (!TRACE) {
+            if (!MASK || out_sem) {
 #pragma unroll
-            for (int ch = 0; ch < 4 * NS4; ++ch)
-                if (ch < S) out_sem[ch * HW + pix] = (ch & 1) ? Cs[ch >> 1].y : Cs[ch >> 1].x;
+                for (int ch = 0; ch < 4 * NS4; ++ch)
+                    if (ch < S) out_sem[ch * HW + pix] = (ch & 1) ? Cs[ch >> 1].y : Cs[ch >> 1].x;
+            }
             out_alpha[pix] = 1 - T;
             out_depth[pix] = C2D.y;
         }
     }
+
+    if (MASK && NS4 > 0) {
+        // Same arithmetic as k_mask_apply (mask.cu) on the values just written to out_sem: fmaf chain over the
+        // channels in order, + bias, first maximum wins.  The staging area is dead by now (every cp.async was
+        // waited for before the last barrier) and becomes the projection table.
+        constexpr int SP = NS4 > 0 ? 4 * NS4 : 1;           // (NS4 == 0 never runs this block)
+        float4* s_w = smem;                                 // [K][NS4]
+        float* s_b = reinterpret_cast<float*>(smem + (size_t)me.K * NS4);
+        float* s_tab = s_b + me.K;
+        __syncthreads();
+        for (int i = tid; i < me.K * SP; i += COMPOSITE_THREADS) {
+            const int k = i / SP, c = i % SP;
+            reinterpret_cast<float*>(s_w)[i] = c < S ? me.mlp_w[(size_t)k * S + c] : 0.f;
+        }
+        for (int i = tid; i < me.K; i += COMPOSITE_THREADS) { s_b[i] = me.mlp_b ? me.mlp_b[i] : 0.f; s_tab[i] = me.sim_table[i]; }
+        __syncthreads();
+        float best = -INFINITY;
+        int bi = 0;
+        for (int k = 0; k < me.K; ++k) {
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < NS4; ++q) {
+                const float4 w4 = s_w[k * NS4 + q];
+                a = fmaf(Cs[2 * q].x, w4.x, a);
+                a = fmaf(Cs[2 * q].y, w4.y, a);
+                a = fmaf(Cs[2 * q + 1].x, w4.z, a);
+                a = fmaf(Cs[2 * q + 1].y, w4.w, a);
+            }
+            const float v = a + s_b[k];
+            if (v > best) { best = v; bi = k; }
+        }
+        if (inside) {
+            const float sv = s_tab[bi];
+            const bool below = sv < me.thresh;
+            me.sim[pix] = below ? 0.f : sv;
+            if (me.bg_mask) me.bg_mask[pix] = below ? 1 : 0;
+            if (me.idx) me.idx[pix] = bi;
+        }
+    }
 }
 
-template <int NS4, bool TRACE>
+template <int NS4, bool TRACE, bool MASK>
 static cudaError_t launch_fwd_t(const goi_view& v, const goi_gaussians& g, const GeomState& gs,
                                 const uint32_t* point_list, uint32_t* cull_out, const ImageState& is, float* out_color,
                                 float* out_sem, float* out_depth, float* out_alpha, const float* img_sem,
-                                float* gau_sem, int32_t* num_gsem, int count_per_channel, cudaStream_t st)
+                                float* gau_sem, int32_t* num_gsem, int count_per_channel, const MaskEpilogue& me,
+                                cudaStream_t st)
 {
     constexpr int BATCH = 128;
     constexpr int ROW = 1 + NS4;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
-    const size_t smem = (size_t)3 * BATCH * (2 + ROW) * sizeof(float4);
-    auto kern = k_composite_fwd<NS4, BATCH, TRACE>;
+    size_t smem = (size_t)3 * BATCH * (2 + ROW) * sizeof(float4);
+    if (MASK) smem = max(smem, (size_t)me.K * NS4 * sizeof(float4) + 2 * (size_t)me.K * sizeof(float));
+    auto kern = k_composite_fwd<NS4, BATCH, TRACE, MASK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
     kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(is.ranges, point_list, v.width, v.height, gx, gs.geo, gs.rgbd,
                                                    g.semantics, g.S, sem_vec, v.background, out_color, out_sem,
                                                    out_depth, out_alpha, is.n_contrib, cull_out, img_sem, gau_sem,
-                                                   num_gsem, count_per_channel);
+                                                   num_gsem, count_per_channel, me);
     count_launches(1);
     return cudaGetLastError();
 }
@@ -247,8 +303,8 @@ cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, cons
                                  const GeomState& gs, const uint32_t* point_list, uint32_t* cull_out,
                                  const ImageState& is, cudaStream_t st)
 {
-#define GOI_FWD(N) return launch_fwd_t<N, false>(v, g, gs, point_list, cull_out, is, out.out_color, out.out_semantic, \
-                                                  out.out_depth, out.out_alpha, nullptr, nullptr, nullptr, 0, st)
+#define GOI_FWD(N) return launch_fwd_t<N, false, false>(v, g, gs, point_list, cull_out, is, out.out_color, out.out_semantic, \
+                                                         out.out_depth, out.out_alpha, nullptr, nullptr, nullptr, 0, MaskEpilogue{}, st)
     switch (sem_groups(g.S)) {
         case 0: GOI_FWD(0);
         case 1: GOI_FWD(1);
@@ -265,8 +321,28 @@ cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float*
                          float* gau_sem, int32_t* num_gsem, int count_per_channel, const GeomState& gs,
                          const uint32_t* point_list, const ImageState& is, cudaStream_t st)
 {
-    return launch_fwd_t<0, true>(v, g, gs, point_list, nullptr, is, out_color, nullptr, nullptr, nullptr, img_sem, gau_sem,
-                                 num_gsem, count_per_channel, st);
+    return launch_fwd_t<0, true, false>(v, g, gs, point_list, nullptr, is, out_color, nullptr, nullptr, nullptr, img_sem,
+                                        gau_sem, num_gsem, count_per_channel, MaskEpilogue{}, st);
+}
+
+// Forward composite + fused mask epilogue: out.out_semantic may be NULL (mask-only render).
+cudaError_t launch_composite_fwd_mask(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
+                                      const goi_mask_args& m, const GeomState& gs, const uint32_t* point_list,
+                                      uint32_t* cull_out, const ImageState& is, cudaStream_t st)
+{
+    const MaskEpilogue me{m.mlp_weight, m.mlp_bias, m.sim_table, m.K, m.thresh, m.sim, m.bg_mask, m.idx};
+#define GOI_FWDM(N) return launch_fwd_t<N, false, true>(v, g, gs, point_list, cull_out, is, out.out_color, out.out_semantic, \
+                                                         out.out_depth, out.out_alpha, nullptr, nullptr, nullptr, 0, me, st)
+    switch (sem_groups(g.S)) {
+        case 0: return cudaErrorInvalidValue;
+        case 1: GOI_FWDM(1);
+        case 2: GOI_FWDM(2);
+        case 3: GOI_FWDM(3);
+        case 4: GOI_FWDM(4);
+        case 8: GOI_FWDM(8);
+        default: GOI_FWDM(16);
+    }
+#undef GOI_FWDM
 }
 
 }  // namespace goi

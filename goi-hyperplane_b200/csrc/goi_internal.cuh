@@ -110,6 +110,11 @@ cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float*
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                                 cudaStream_t st);
 cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st);
+cudaError_t launch_mask_table(const goi_mask_args& a, cudaStream_t st);
+cudaError_t launch_mask_zero_input(const goi_mask_args& a, cudaStream_t st);   // x == 0 everywhere; table already built
+cudaError_t launch_composite_fwd_mask(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
+                                      const goi_mask_args& m, const GeomState& gs, const uint32_t* point_list,
+                                      uint32_t* cull_out, const ImageState& is, cudaStream_t st);
 
 // ---- small device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -139,10 +139,45 @@ static cudaError_t launch_mask_t(const goi_mask_args& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
+cudaError_t launch_mask_table(const goi_mask_args& a, cudaStream_t st)
 {
     k_mask_table<<<a.K, 128, 0, st>>>(a.K, a.D, a.mode, a.lut, a.hyperplane_w, a.hyperplane_b, a.log_scale, a.sim_table);
-    cudaError_t e = cudaGetLastError();
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+// All-zero input (an empty scene rendered through the fused epilogue): logits = biases for every element.
+__global__ void __launch_bounds__(256) k_mask_zero_input(int64_t N, int K, const float* __restrict__ mlp_b,
+                                                         const float* __restrict__ sim_table, float thresh,
+                                                         float* __restrict__ sim, uint8_t* __restrict__ bg_mask,
+                                                         int32_t* __restrict__ idx_out)
+{
+    float best = -INFINITY;
+    int bi = 0;
+    for (int k = 0; k < K; ++k) {
+        const float v = 0.f + (mlp_b ? mlp_b[k] : 0.f);
+        if (v > best) { best = v; bi = k; }
+    }
+    const float s = sim_table[bi];
+    const bool bg = s < thresh;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        sim[i] = bg ? 0.f : s;
+        if (bg_mask) bg_mask[i] = bg ? 1 : 0;
+        if (idx_out) idx_out[i] = bi;
+    }
+}
+
+cudaError_t launch_mask_zero_input(const goi_mask_args& a, cudaStream_t st)
+{
+    if (a.N <= 0) return cudaSuccess;
+    k_mask_zero_input<<<148 * 4, 256, 0, st>>>(a.N, a.K, a.mlp_bias, a.sim_table, a.thresh, a.sim, a.bg_mask, a.idx);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
+{
+    cudaError_t e = launch_mask_table(a, st);
     if (e != cudaSuccess) return e;
     if (a.N <= 0) return cudaSuccess;
     switch (sem_groups(a.S)) {

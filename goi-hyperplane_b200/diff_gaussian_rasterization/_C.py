@@ -25,7 +25,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GOI_RASTER_LIB", os.path.join(_HERE, "..", "lib", "libgoi_raster.so"))
-GOI_ABI_VERSION = 3
+GOI_ABI_VERSION = 4
 GOI_MAX_SEM = 64
 GOI_MASK_APE, GOI_MASK_OSH = 0, 1
 GOI_RAW_OPACITY, GOI_RAW_SCALE, GOI_RAW_ROTATION = 1, 2, 4
@@ -104,6 +104,9 @@ SYMBOLS = {
                             ALLOC_FN, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "goi_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "goi_mask": (C.c_int, [C.POINTER(goi_mask_args), C.c_void_p]),
+    "goi_forward_mask": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
+                                   C.POINTER(goi_mask_args), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int64)]),
     "goi_read_stats": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.POINTER(goi_stats)]),
     "goi_timing_enable": (C.c_int, [C.c_int]),
@@ -421,6 +424,66 @@ def hyperplane_mask(x, mlp_weight, mlp_bias, lut, hyperplane_w, hyperplane_b=0.0
                           bg.data_ptr() if N else None, idx.data_ptr() if (want_idx and N) else None)
         _check(L.goi_mask(C.byref(a), _stream(dev)), "goi_mask")
     return sim, bg, idx
+
+
+def rasterize_gaussians_mask(bg, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
+                             cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                             degree, campos, prefiltered, debug, mlp_weight, mlp_bias, lut, hyperplane_w,
+                             hyperplane_b=0.0, log_scale=0.0, thresh=0.86, mode=GOI_MASK_APE, want_semantics=True,
+                             want_idx=False):
+    """Forward render + open-vocabulary mask in ONE pass (goi_forward_mask).  Inference
+    only.  Returns (color, semantic or None, depth, alpha, radii, sim[H,W], bg_mask[H,W] bool, idx[H,W] or None);
+    with want_semantics=False the [S,H,W] semantic image is never materialised."""
+    L = lib()
+    keep = []
+    dev = means3D.device
+    with torch.cuda.device(dev):
+        g, means3D = _make_gaussians(means3D, sh, colors, semantics, opacity, scales, rotations, cov3D_precomp, keep)
+        view = _make_view(bg, viewmatrix, projmatrix, campos, image_width, image_height, tan_fovx, tan_fovy,
+                          scale_modifier, degree, prefiltered, debug, keep)
+        if g.P == 0:                       # an empty [0,S] tensor travels as NULL: take S from the projection
+            g.S = int(mlp_weight.shape[1])
+        P, S, H, W = g.P, g.S, int(image_height), int(image_width)
+        if S <= 0:
+            raise RuntimeError("the fused mask needs semantic channels")
+        f32 = dict(dtype=torch.float32, device=dev)
+        out_color = torch.empty((3, H, W), **f32)
+        out_sem = torch.empty((S, H, W), **f32) if want_semantics else None
+        out_depth = torch.empty((1, H, W), **f32)
+        out_alpha = torch.empty((1, H, W), **f32)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        w, lut_ = _f32(mlp_weight, "mlp_weight"), _f32(lut, "lut")
+        b = _f32(mlp_bias, "mlp_bias")
+        hw = _f32(hyperplane_w.reshape(-1), "hyperplane_w")
+        K, D = lut_.shape
+        if w.shape != (K, S):
+            raise RuntimeError(f"mlp_weight must be [{K},{S}], got {tuple(w.shape)}")
+        sim = torch.empty((H, W), **f32)
+        bgm = torch.empty((H, W), dtype=torch.bool, device=dev)
+        idx = torch.empty((H, W), dtype=torch.int32, device=dev) if want_idx else None
+        table = torch.empty((K,), **f32)
+        m = goi_mask_args(H * W, S, K, D, int(mode), 1, H * W, None, _ptr(w), _ptr(b), _ptr(lut_), _ptr(hw),
+                          float(hyperplane_b), float(log_scale), float(thresh), _ptr(table), _ptr(sim),
+                          bgm.data_ptr(), idx.data_ptr() if want_idx else None)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        geom_bytes, img_bytes = L.goi_geom_bytes(P, S), L.goi_image_bytes(W, H)
+        geom, img = torch.empty((geom_bytes,), **u8), torch.empty((img_bytes,), **u8)
+        stream = _stream(dev)
+        R = C.c_int64(0)
+        out = goi_fwd_out(_ptr(out_color), _ptr(out_sem), _ptr(out_depth), _ptr(out_alpha), _ptr(radii))
+        global _r_guess
+        bin_bytes = L.goi_binning_bytes(max(int(_r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
+        binning = torch.empty((bin_bytes,), **u8)
+        args = (C.byref(view), C.byref(g), C.byref(out), C.byref(m), geom.data_ptr(), geom_bytes)
+        rc = L.goi_forward_mask(*args, binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, stream, C.byref(R))
+        if rc == -3 and R.value > 0 and L.goi_binning_bytes(R.value) > bin_bytes:
+            bin_bytes = L.goi_binning_bytes(R.value)
+            binning = torch.empty((bin_bytes,), **u8)
+            rc = L.goi_forward_mask(*args, binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, stream,
+                                    C.byref(R))
+        _check(rc, "goi_forward_mask")
+        _r_guess = max(R.value, int(0.9 * _r_guess))
+    return out_color, out_sem, out_depth, out_alpha, radii, sim, bgm, idx
 
 
 def timing_enable(on: bool) -> None:

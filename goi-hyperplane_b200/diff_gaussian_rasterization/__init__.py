@@ -235,6 +235,30 @@ class GaussianRasterizer(nn.Module):
         return _RasterizeGaussiansRaw.apply(means3D, means2D, features_dc, features_rest, semantics, opacity_logits,
                                             log_scales, raw_rotations, self.raster_settings)
 
+    @torch.no_grad()
+    def forward_mask(self, means3D, opacities, hyperplane, shs=None, colors_precomp=None, semantics=None, scales=None,
+                     rotations=None, cov3D_precomp=None, want_semantics=True, want_idx=False):
+        """Inference render + open-vocabulary mask in one pass (not in the reference):
+        equals ``forward(...)`` followed by ``hyperplane.compute_similarity(semantic_image)`` (gui/main.py:588-590,
+        363-385) with the mask evaluated in the composite kernel's epilogue.  ``hyperplane`` is a
+        ``goi_b200.semantic_mask.SemanticHyperplane``.  Returns a dict: render, semantics (None when
+        want_semantics=False -- the [S,H,W] image is then never written), depth, alpha, radii, sim [H,W] (zeros
+        below the threshold), bg_mask [H,W] bool, idx [H,W] int32 or None."""
+        rs = self.raster_settings
+        self._check_inputs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        e = torch.Tensor([])
+        mode, thresh, bias = hyperplane.kernel_args()
+        color, sem, depth, alpha, radii, sim, bg, idx = _C.rasterize_gaussians_mask(
+            rs.bg, means3D, e if colors_precomp is None else colors_precomp, semantics, opacities,
+            e if scales is None else scales, e if rotations is None else rotations, rs.scale_modifier,
+            e if cov3D_precomp is None else cov3D_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+            rs.image_height, rs.image_width, e if shs is None else shs, rs.sh_degree, rs.campos, rs.prefiltered,
+            rs.debug, hyperplane.mlp_weight, hyperplane.mlp_bias, hyperplane.lut, hyperplane.w, hyperplane_b=bias,
+            log_scale=hyperplane.log_scale, thresh=thresh, mode=mode, want_semantics=want_semantics,
+            want_idx=want_idx)
+        return {"render": color, "semantics": sem, "depth": depth, "alpha": alpha, "radii": radii, "sim": sim,
+                "bg_mask": bg, "idx": idx}
+
     def trace(self, means3D, means2D, opacities, shs=None, colors_precomp=None, img_sem=None, scales=None,
               rotations=None, cov3D_precomp=None):
         raster_settings = self.raster_settings

@@ -130,6 +130,25 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
             "radii": radii}
 
 
+@torch.no_grad()
+def render_mask(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, hyperplane, scaling_modifier=1.0,
+                override_color=None, want_semantics=True, want_idx=False):
+    """``render`` + ``GUI.compute_similarity`` on the rendered semantic image in one pass (the GUI's test_step,
+    reference gui/main.py:575-600 with :363-385), using the composite kernel's fused mask epilogue.  Inference
+    only.  Adds ``sim`` [H,W], ``bg_mask`` [H,W] and ``mask`` (= sim > 0, gui/main.py:396) to the render dict;
+    ``semantics`` is None when want_semantics=False."""
+    rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, pc, pipe, bg_color, scaling_modifier))
+    scales, rotations, cov3D_precomp, shs, colors_precomp = _marshal(viewpoint_camera, pc, pipe, scaling_modifier,
+                                                                     override_color)
+    out = rasterizer.forward_mask(means3D=pc.get_xyz, opacities=pc.get_opacity, hyperplane=hyperplane, shs=shs,
+                                  colors_precomp=colors_precomp, semantics=pc.get_semantics, scales=scales,
+                                  rotations=rotations, cov3D_precomp=cov3D_precomp, want_semantics=want_semantics,
+                                  want_idx=want_idx)
+    out["visibility_filter"] = out["radii"] > 0
+    out["mask"] = out["sim"] > 0
+    return out
+
+
 def trace(viewpoint_camera, pc, img_sem: torch.Tensor, pipe, bg_color: torch.Tensor, scaling_modifier=1.0,
           override_color=None):
     """Back-project a 2D feature image onto the Gaussians (reference :107-192)."""

@@ -39,13 +39,16 @@ class SemanticHyperplane:
         self.svm_bias = (2 - inverse_sigmoid(set_bias)) if bias is None else float(bias)
         return self
 
+    def kernel_args(self):
+        """(mode, threshold, bias) of the active head: OSH uses 0.5 (gui/main.py:377-378), APE self.thresh."""
+        if self.res_finetuned:
+            return _C.GOI_MASK_OSH, 0.5, self.svm_bias
+        return _C.GOI_MASK_APE, self.thresh, 0.0
+
     @torch.no_grad()
     def compute_similarity(self, embedding_feature, out_bg_mask=None, channels_first=False, want_idx=False):
         """gui/main.py:363-385: returns sim with below-threshold entries zeroed; fills out_bg_mask."""
-        if self.res_finetuned:
-            mode, thresh, bias = _C.GOI_MASK_OSH, 0.5, self.svm_bias
-        else:
-            mode, thresh, bias = _C.GOI_MASK_APE, self.thresh, 0.0
+        mode, thresh, bias = self.kernel_args()
         sim, bg, idx = _C.hyperplane_mask(embedding_feature, self.mlp_weight, self.mlp_bias, self.lut, self.w,
                                           hyperplane_b=bias, log_scale=self.log_scale, thresh=thresh, mode=mode,
                                           channels_first=channels_first, want_idx=want_idx)

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GOI_ABI_VERSION 3
+#define GOI_ABI_VERSION 4
 #define GOI_MAX_SEM 64          /* largest supported semantic channel count */
 #define GOI_TILE 16             /* tile edge in pixels (config.h:16-17 BLOCK_X/Y) */
 
@@ -279,6 +279,19 @@ typedef struct goi_mask_args {
     int32_t* idx;               /* [N] out or NULL                             */
 } goi_mask_args;
 int goi_mask(const goi_mask_args* args, void* stream);
+
+/* ---- forward + mask in one pass (the reference renders, permutes the
+ * [S,H,W] image to [HW,S] and then runs compute_similarity on it, gui/main.py:588-590, 363-385).
+ * Same contract as goi_forward_auto, plus: the composite kernel evaluates the mask of every pixel in its
+ * epilogue, while the pixel's S semantic accumulators are still in registers.  mask->x / stride_n /
+ * stride_c are ignored, mask->N must be width*height and mask->S == g->S > 0; sim / bg_mask / idx are
+ * [H*W].  out->out_semantic may be NULL: the semantic image is then never written to memory (a
+ * mask-only render saves its 4*S*N bytes of writes and the mask pass's 4*S*N bytes of reads).
+ * Results are bit-identical to goi_forward_auto followed by goi_mask on its out_semantic. */
+int goi_forward_mask(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
+                     const goi_mask_args* mask,
+                     void* geom_buf, size_t geom_bytes, void* binning_buf, size_t binning_bytes,
+                     void* image_buf, size_t image_bytes, void* stream, int64_t* num_rendered);
 
 /* ---- introspection used by bench.py / tests (device->host copies, syncs). */
 typedef struct goi_stats {

@@ -82,3 +82,61 @@ def test_mask_from_render_and_gaussian_selection():
     assert float(agree) > 0.999
     sel = hp.select_gaussians(g.get_semantics.cuda())
     assert sel.shape == (P,) and 0 < int(sel.sum()) < P
+
+
+@pytest.mark.parametrize("S,mode,want_sem", [(16, "ape", True), (16, "ape", False), (10, "osh", True),
+                                             (32, "ape", False), (4, "osh", False)])
+def test_fused_mask_epilogue_equals_render_then_mask(S, mode, want_sem):
+    """goi_forward_mask == goi_forward followed by goi_mask, bit for bit, and against the
+    oracle's mask of the oracle-independent rendered features."""
+    from gaussian_renderer import render, render_mask
+    from goi_b200.scenes import PipeFlags
+    P, W, H = 30_000, 333, 207                      # ragged: W, H not multiples of the 16-pixel tile
+    g, cam, bg = make_scene(P, W, H, S, 50 + S)
+    g, cam, bg = g.to("cuda"), cam.to("cuda"), bg.to("cuda")
+    mlp_w, mlp_b, lut, w = make_mask_model(S, seed=S)
+    hp = SemanticHyperplane(mlp_w.cuda(), mlp_b.cuda(), lut.cuda(), w.cuda(), log_scale=0.1, thresh=0.86)
+    if mode == "osh":
+        hp.enable_osh()
+    with torch.no_grad():
+        base = render(cam, g, PipeFlags(), bg)
+        bg_ref = torch.zeros(H * W, dtype=torch.bool, device="cuda")
+        sim_ref, idx_ref = hp.compute_similarity(base["semantics"], out_bg_mask=bg_ref, channels_first=True,
+                                                 want_idx=True)
+    out = render_mask(cam, g, PipeFlags(), bg, hp, want_semantics=want_sem, want_idx=True)
+    assert torch.equal(out["render"], base["render"]) and torch.equal(out["depth"], base["depth"])
+    assert torch.equal(out["alpha"], base["alpha"]) and torch.equal(out["radii"], base["radii"])
+    if want_sem:
+        assert torch.equal(out["semantics"], base["semantics"])
+    else:
+        assert out["semantics"] is None
+    assert torch.equal(out["idx"].view(-1), idx_ref)
+    assert torch.equal(out["sim"].view(-1), sim_ref)
+    assert torch.equal(out["bg_mask"].view(-1), bg_ref)
+    assert out["mask"].shape == (H, W) and 0 < int(out["mask"].sum()) < H * W
+    # and against the CPU oracle's mask on the same rendered features
+    kw = dict(mode=0, log_scale=0.1, thresh=0.86) if mode == "ape" else dict(mode=1, hyperplane_b=hp.svm_bias, thresh=0.5)
+    o = oracle.mask(base["semantics"].permute(1, 2, 0).reshape(-1, S).cpu().numpy(), mlp_w.numpy(), mlp_b.numpy(),
+                    lut.numpy(), w.numpy(), **kw)
+    clear = o["top2_gap"] > 1e-4
+    assert np.array_equal(out["idx"].view(-1).cpu().numpy()[clear], o["idx"][clear])
+    assert np.abs(out["sim"].view(-1).cpu().numpy()[clear] - o["sim"][clear]).max() <= 1e-4
+
+
+def test_fused_mask_on_an_empty_scene():
+    """P == 0: nothing is rendered; every pixel's feature vector is zero, so the logits are the biases."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    S, W, H = 8, 64, 48
+    _, cam, bg = make_scene(10, W, H, S, 1)
+    cam, bg = cam.to("cuda"), bg.to("cuda")
+    mlp_w, mlp_b, lut, w = make_mask_model(S, seed=3)
+    hp = SemanticHyperplane(mlp_w.cuda(), mlp_b.cuda(), lut.cuda(), w.cuda(), thresh=0.5)
+    rs = GaussianRasterizationSettings(H, W, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), bg, 1.0,
+                                       cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center,
+                                       False, False)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    out = GaussianRasterizer(rs).forward_mask(z(0, 3), z(0, 1), hp, shs=z(0, 16, 3), semantics=z(0, S),
+                                              scales=z(0, 3), rotations=z(0, 4), want_idx=True)
+    sim_ref, idx_ref = hp.compute_similarity(z(H * W, S), want_idx=True)
+    assert torch.equal(out["idx"].view(-1), idx_ref) and torch.equal(out["sim"].view(-1), sim_ref)
+    assert float(out["semantics"].abs().max()) == 0.0 and float(out["render"].abs().max()) == 0.0
