@@ -111,6 +111,23 @@ def make_views(W, H, device):
     return cams
 
 
+def ncu_reference(config):
+    """DRAM bytes and executed warp instructions of the two composite kernels from the committed `ncu --set full`
+    capture (profiles/traffic.json), for roofline.traffic and the issue-slot companion bound; None if the capture
+    is of another config."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        if d.get("config") != config:
+            return None
+        ks = d["kernels"].values()
+        return {"dram_bytes": sum(k["dram_bytes"] for k in ks),
+                "warp_instructions": sum(k["warp_instructions"] for k in ks), "source": d["source"]}
+    except Exception:
+        return None
+
+
 def b_comp(R, W, H, S):
     """algorithmic bytes of forward + backward composite for one view."""
     T = ((W + 15) // 16) * ((H + 15) // 16)
@@ -289,6 +306,18 @@ def run_ours(args):
                      "algorithmic_bytes_per_view": int(bytes_comp), "kernel_ms_per_view": round(t_comp * 1e3, 4)},
         "stages_ms_per_view": {k: round(v / args.steps, 4) for k, v in stage_acc.items()},
     }
+    ref = ncu_reference(args.config)
+    if ref is not None and t_comp > 0:
+        # measured DRAM traffic of the same two launches (ncu), and the bound that actually limits them: warp
+        # instruction issue (4 schedulers x 1 instruction/clk per SM).  ncu's instruction count / this run's time.
+        line["roofline"]["traffic"] = ref["dram_bytes"]
+        line["roofline"]["traffic_source"] = ref["source"]
+        sm_clk = (clocks.get("sm_mhz") or 1965) * 1e6
+        issue_peak = 148 * 4 * sm_clk
+        line["roofline"]["issue_bound"] = {
+            "achieved": round(ref["warp_instructions"] / t_comp / 1e9, 1), "peak": round(issue_peak / 1e9, 1),
+            "unit": "G warp-instructions/s", "frac": round(ref["warp_instructions"] / t_comp / issue_peak, 4),
+            "note": "composites are issue-bound, not HBM-bound (DESIGN.md section 4); FFMA2 counts once but takes two slots"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
