@@ -17,9 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "lib", "libgoi_raster.so")
+LIB_SEMLOSS = os.path.join(HERE, "lib", "libgoi_semloss.so")      # fused training loss (links cuBLAS for its two plain GEMMs)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "composite_fwd.cu", "composite_bwd.cu", "mask.cu"]
-HEADERS = [os.path.join(CSRC, "goi_internal.cuh"), os.path.join(HERE, "..", "include", "goi_raster.h")]
+HEADERS = [os.path.join(CSRC, "goi_internal.cuh"), os.path.join(CSRC, "goi_cull.cuh"),
+           os.path.join(HERE, "..", "include", "goi_raster.h"), os.path.join(HERE, "..", "include", "goi_semloss.h")]
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -58,7 +60,22 @@ def build(force: bool = False, verbose: bool = False, stats: bool = False) -> st
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
                "-Xcompiler", "-fPIC", *objs, "-o", lib]
         subprocess.run(cmd, check=True)
+    if not stats:
+        build_semloss(force, verbose)
     return lib
+
+
+def build_semloss(force: bool = False, verbose: bool = False) -> str:
+    """libgoi_semloss.so: csrc/semloss.cu + cuBLAS (dynamic, soname libcublas.so.12: the copy torch already loaded, or
+    the toolkit's via the rpath).  Kept apart from libgoi_raster.so so the rasterizer stays dependency-free."""
+    obj = _compile("semloss.cu", force, verbose)
+    if force or _stale(LIB_SEMLOSS, [obj]):
+        cuda_lib = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(NVCC))), "lib64")
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+               "-Xcompiler", "-fPIC", obj, "-o", LIB_SEMLOSS, f"-L{cuda_lib}", "-lcublas",
+               "-Xlinker", f"-rpath={cuda_lib}"]
+        subprocess.run(cmd, check=True)
+    return LIB_SEMLOSS
 
 
 if __name__ == "__main__":

@@ -1,0 +1,148 @@
+"""Training-side semantic loss.
+
+CPU: the oracle restatement (oracle/semloss_oracle.py) against golden vectors produced by the reference's own source
+lines (tests/golden/make_semloss_golden.py), and the C ABI of libgoi_semloss.so.  GPU: the fused CUDA path against
+the oracle and the goldens through the C ABI / autograd surface."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.semloss_oracle import semantic_loss_reference
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "semloss_*.npz")))
+TERMS = ("loss", "lab", "sl", "sl1", "recc")
+GRADS = ("d_sem_feature", "d_mlp_weight", "d_mlp_bias", "d_lut")
+LOSS_RTOL = 1e-5        # loss terms: relative (fp32 sums over N*K elements)
+GRAD_RTOL = 1e-3        # gradients: max|a-b| <= 1e-3 max|ref| per tensor (the north-star gradient criterion)
+
+
+def load(path):
+    z = np.load(path)
+    H, W, S, K, D, it, seed = [int(v) for v in z["meta"]]
+    t = lambda k: torch.from_numpy(z[k].astype(np.float32))
+    x = t("sem_feature").permute(1, 2, 0).reshape(-1, S)                   # train.py:142
+    gt = t("ape").permute(1, 2, 0).reshape(-1, D)                          # train.py:147
+    return z, dict(H=H, W=W, S=S, K=K, D=D, it=it), x, gt, t
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_oracle_matches_reference_source_golden(path, dtype):
+    assert GOLD, "golden fixtures missing"
+    z, m, x, gt, t = load(path)
+    o = semantic_loss_reference(x, t("mlp_weight"), t("mlp_bias"), t("lut"), gt, t=1.0 if m["it"] < 1000 else 2.0,
+                                dtype=dtype)
+    for k in TERMS:
+        assert abs(float(o[k]) - float(z[k])) <= 2e-5 * max(1.0, abs(float(z[k]))), k
+    assert rel(o["d_sem_feature"].reshape(m["H"], m["W"], m["S"]).permute(2, 0, 1).numpy(), z["d_sem_feature"]) <= 2e-4
+    for k in GRADS[1:]:
+        assert rel(o[k].numpy(), z[k]) <= 2e-4, k
+
+
+def test_semloss_library_exports_every_declared_symbol():
+    from goi_b200 import semantic_loss as sl
+    header = open(os.path.join(ROOT, "include", "goi_semloss.h")).read()
+    declared = set(re.findall(r"\b(goi_sem\w+)\s*\(", header))
+    assert declared == set(sl.SYMBOLS), (declared, set(sl.SYMBOLS))
+    L = sl.lib()                                       # loads, binds every symbol, checks the ABI version
+    assert L.goi_semloss_abi_version() == sl.GOI_SEMLOSS_ABI_VERSION
+    assert L.goi_semloss_workspace_bytes(1000, 300, 256) >= 4 * (1000 * 300 + 1000 + 2 * 300 * 256)
+    # argument validation needs no GPU
+    a = sl.goi_semloss_args()
+    assert L.goi_semantic_loss(C.byref(a), None) == -1
+    assert b"bad N/S/K/D" in L.goi_semloss_last_error()
+    assert C.sizeof(sl.goi_semloss_args) == 152          # static_assert-ed in csrc/semloss.cu
+
+
+def test_product_never_imports_the_oracle():
+    src = open(os.path.join(ROOT, "goi-hyperplane_b200", "goi_b200", "semantic_loss.py")).read()
+    assert "oracle" not in src.replace("no CPU/eager fallback", "")
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def run_cuda(x, W, b, lut, gt, it, planar_hw=None, precision=0):
+    from goi_b200.semantic_loss import semantic_loss
+    dev = "cuda"
+    W_, b_, lut_ = (v.to(dev).clone().requires_grad_(True) for v in (W, b, lut))
+    if planar_hw is not None:
+        H, Wd = planar_hw
+        xs = x.reshape(H, Wd, -1).permute(2, 0, 1).contiguous().to(dev).requires_grad_(True)     # [S,H,W] like the render
+        g = gt.reshape(H, Wd, -1).permute(2, 0, 1).contiguous().to(dev)                          # [D,H,W] like the dataset
+    else:
+        xs, g = x.to(dev).clone().requires_grad_(True), gt.to(dev)
+    loss, terms = semantic_loss(xs, (W_, b_), lut_, g, iteration=it, precision=precision)
+    loss.backward()
+    torch.cuda.synchronize()
+    dx = xs.grad
+    if planar_hw is not None:
+        dx = dx.permute(1, 2, 0).reshape(x.shape)
+    tv = terms.cpu().numpy()
+    return dict(loss=tv[0], lab=tv[1], sl=tv[2], sl1=tv[3], recc=tv[4], min_sim_val=tv[5], d_sem_feature=dx.cpu(),
+                d_mlp_weight=W_.grad.cpu(), d_mlp_bias=b_.grad.cpu(), d_lut=lut_.grad.cpu())
+
+
+def check(cu, ref, loss_rtol=LOSS_RTOL, grad_rtol=GRAD_RTOL):
+    for k in TERMS:
+        assert abs(float(cu[k]) - float(ref[k])) <= loss_rtol * max(1.0, abs(float(ref[k]))), (k, float(cu[k]), float(ref[k]))
+    for k in GRADS:
+        r = rel(cu[k].numpy(), np.asarray(ref[k]).reshape(cu[k].shape))
+        assert r <= grad_rtol, (k, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+@pytest.mark.parametrize("planar", [False, True])
+def test_cuda_matches_reference_source_golden(path, planar):
+    z, m, x, gt, t = load(path)
+    cu = run_cuda(x, t("mlp_weight"), t("mlp_bias"), t("lut"), gt, m["it"], (m["H"], m["W"]) if planar else None)
+    ref = {k: z[k] for k in TERMS}
+    ref["d_sem_feature"] = torch.from_numpy(z["d_sem_feature"]).permute(1, 2, 0).reshape(-1, m["S"]).numpy()
+    for k in GRADS[1:]:
+        ref[k] = z[k]
+    check(cu, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,S,K,D,it", [(4099, 16, 300, 256, 1), (2500, 10, 300, 256, 2000), (777, 32, 512, 64, 5),
+                                        (33, 3, 5, 8, 1), (1, 16, 300, 256, 1)])
+def test_cuda_matches_oracle(N, S, K, D, it):
+    g = torch.Generator().manual_seed(N + S)
+    x = torch.randn(N, S, generator=g)
+    W, b = torch.randn(K, S, generator=g) * 0.4, torch.randn(K, generator=g) * 0.1
+    lut = torch.randn(K, D, generator=g) * 0.5 + 0.1
+    gt = lut[torch.randint(0, K, (N,), generator=g)] + 0.3 * torch.randn(N, D, generator=g)
+    ref = semantic_loss_reference(x, W, b, lut, gt, t=1.0 if it < 1000 else 2.0, dtype=torch.float64)
+    cu = run_cuda(x, W, b, lut, gt, it)
+    check(cu, {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in ref.items()})
+    assert abs(float(cu["min_sim_val"]) - float(ref["min_sim_val"])) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_tf32_gemms_stay_close_and_scale_with_upstream_gradient():
+    N, S, K, D = 20000, 16, 300, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, S, generator=g)
+    W, b = torch.randn(K, S, generator=g) * 0.4, torch.randn(K, generator=g) * 0.1
+    lut = torch.randn(K, D, generator=g) * 0.5 + 0.1
+    gt = lut[torch.randint(0, K, (N,), generator=g)] + 0.3 * torch.randn(N, D, generator=g)
+    a = run_cuda(x, W, b, lut, gt, 1, precision=0)
+    c = run_cuda(x, W, b, lut, gt, 1, precision=1)
+    # TF32 rounds the GEMM inputs to 10 mantissa bits: loss terms to ~1e-3, label flips on near-ties allowed
+    check(c, {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in a.items()}, loss_rtol=2e-3, grad_rtol=5e-2)
+    # upstream gradient scaling through autograd (loss * 3).backward()
+    from goi_b200.semantic_loss import semantic_loss
+    xs = x.cuda().requires_grad_(True)
+    loss, _ = semantic_loss(xs, (W.cuda(), b.cuda()), lut.cuda(), gt.cuda(), iteration=1)
+    (3.0 * loss).backward()
+    assert rel(xs.grad.cpu().numpy(), 3.0 * a["d_sem_feature"].numpy()) <= 1e-5
