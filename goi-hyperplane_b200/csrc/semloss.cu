@@ -40,8 +40,6 @@ constexpr int ERR_INVALID = -1, ERR_CUDA = -2, ERR_WORKSPACE = -3, ERR_UNSUPPORT
 
 constexpr int ROWS_THREADS = 256;
 constexpr int PB = 32;                 // pixels per CTA batch (4 per warp)
-constexpr int KI_MAX = GOI_SEMLOSS_MAX_K / 32;
-constexpr int KT = GOI_SEMLOSS_MAX_K / ROWS_THREADS;
 
 struct Accum {                         // double accumulators of the loss terms + the min (ordered-int encoded)
     double lab, simval, ent, rec;
@@ -56,12 +54,6 @@ __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v)
-{
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 // max with FIRST index on ties (torch.argmax / max(dim) convention used by the oracle)
@@ -133,10 +125,42 @@ __global__ void __launch_bounds__(256) k_gt_inv_norms(int64_t N, int D, int plan
     }
 }
 
+// Warp-wide sums of N per-lane partial values with a transposing butterfly: while more than one value is left,
+// a step at lane distance `off` exchanges halves (lanes with bit `off` set keep the upper half) -- N/2 + N/4 + ...
+// shuffles -- and the remaining steps are plain all-reduce steps on the single survivor.  N = 32: 31 shuffles,
+// element c ends in lane c.  N = 16: 16 shuffles, element c ends in lanes 2c and 2c+1.  (5 N shuffles otherwise.)
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane)
+{
+    int n = N;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k)
+                if (k < n / 2) {
+                    const float lo = v[k], hi = v[k + n / 2];
+                    const float send = upper ? lo : hi;
+                    const float keep = upper ? hi : lo;
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            n >>= 1;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ int dx_channel(int lane, int n) { return n == 32 ? lane : (lane >> 1); }
+
 // One pass per pixel over its similarity row; see the header of this file.
-// Phase A: a warp owns a pixel, lane l owns codebook rows k = l, l+32, ... (values in registers).
+// Phase A: a warp owns a pixel, lane l owns codebook rows k = l, l+32, ... (KI values per lane, in registers); the
+//          next pixel's similarity row is prefetched while the current one is processed.
 // Phase B: the CTA turns the PB staged dz rows into its running dW / db accumulators (thread t owns rows t, t+256).
-template <int NS4>
+// exp/log are ex2/lg2.approx (2 ulp): they produce softmax weights that enter sums of K terms; decisions (arg-max,
+// label equality) never depend on them.
+template <int NS4, int KI>
 __global__ void __launch_bounds__(ROWS_THREADS, (NS4 <= 4 ? 2 : 1))
 k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
                float* __restrict__ G, const float* __restrict__ inv_norm, const float* __restrict__ W,
@@ -145,6 +169,9 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
 {
     constexpr int SP = 4 * NS4;                 // padded channels
     constexpr int WS = SP + 4;                  // row stride of the staged weights: LDS.128 conflict-free
+    constexpr int KTT = (KI * 32 + ROWS_THREADS - 1) / ROWS_THREADS;   // codebook rows per thread in phase B
+    constexpr int DXN = SP <= 16 ? 16 : 32;     // dx reduction width
+    constexpr int PPW = PB / 8;                 // pixels per warp per batch
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);               // [K][WS]
     float* s_b = s_w + (size_t)K * WS;                          // [K]
@@ -152,7 +179,6 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
     float* s_dz = s_x + PB * SP;                                // [PB][KP]
     const int KP = (K + 31) & ~31;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KI = (K + 31) >> 5;
 
     for (int i = tid; i < K * SP; i += ROWS_THREADS) {
         const int k = i / SP, c = i % SP;
@@ -165,9 +191,9 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
     const float cl = 100.0f / ((float)N * (float)K);            // d(50 * MSE)/d(P') = 2 * 50 / (N K) * (P' - L)
     const float ce = 0.3f * t_anneal * invN;
 
-    float accw[KT][SP], accb[KT];
+    float accw[KTT][SP], accb[KTT];
 #pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
+    for (int kk = 0; kk < KTT; ++kk) {
         accb[kk] = 0.f;
 #pragma unroll
         for (int c = 0; c < SP; ++c) accw[kk][c] = 0.f;
@@ -176,19 +202,39 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
     float l_min = INFINITY;
 
     const int64_t nbatch = (N + PB - 1) / PB;
+    // prefetch registers: raw similarity row + 1/|gt| of the warp's next pixel
+    float gn[KI], invn = 0.f;
+    auto prefetch = [&](int64_t p) {
+        if (p < N) {
+            invn = inv_norm[p];
+            const float* r = G + (size_t)p * K;
+#pragma unroll
+            for (int i = 0; i < KI; ++i) gn[i] = (lane + 32 * i < K) ? r[lane + 32 * i] : 0.f;
+        }
+    };
+    prefetch((int64_t)blockIdx.x * PB + warp * PPW);
+
     for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
-        // ---------------- phase A: 4 pixels per warp ----------------
-        for (int pp = 0; pp < PB / 8; ++pp) {
-            const int pl = warp * (PB / 8) + pp;                 // pixel slot in the batch
+        // ---------------- phase A ----------------
+        for (int pp = 0; pp < PPW; ++pp) {
+            const int pl = warp * PPW + pp;                      // pixel slot in the batch
             const int64_t p = bt * PB + pl;
             float* dzrow = s_dz + (size_t)pl * KP;
             float* xrow = s_x + pl * SP;
+            const int64_t pnext = (pp + 1 < PPW) ? p + 1 : (bt + gridDim.x) * PB + warp * PPW;
             if (p >= N) {                                        // ragged tail: contributes nothing
                 for (int k = lane; k < KP; k += 32) dzrow[k] = 0.f;
                 for (int c = lane; c < SP; c += 32) xrow[c] = 0.f;
+                prefetch(pnext);
                 continue;
             }
             for (int c = lane; c < SP; c += 32) xrow[c] = c < S ? x[p * xs_n + c * xs_c] : 0.f;
+            // this pixel's prefetched row -> sim, then start the next pixel's loads
+            float sm[KI];
+            const float inv = invn;
+#pragma unroll
+            for (int i = 0; i < KI; ++i) sm[i] = gn[i] * inv;
+            prefetch(pnext);
             __syncwarp();
             float xs[SP];
 #pragma unroll
@@ -196,107 +242,109 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
                 const float4 v = reinterpret_cast<const float4*>(xrow)[q];
                 xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
             }
-            const float inv = inv_norm[p];
             float* grow = G + (size_t)p * K;
 
-            // logits and similarities of this lane's codebook rows
-            float z[KI_MAX], sm[KI_MAX];
+            // logits of this lane's codebook rows; row maxima with the FIRST index on ties
+            float z[KI];
             float zmax = -INFINITY, smax = -INFINITY;
             int zarg = 0, sarg = 0;
 #pragma unroll
-            for (int i = 0; i < KI_MAX; ++i) {
-                z[i] = -INFINITY; sm[i] = -INFINITY;
-                if (i < KI) {
-                    const int k = lane + 32 * i;
-                    if (k < K) {
-                        float a = 0.f;
+            for (int i = 0; i < KI; ++i) {
+                const int k = lane + 32 * i;
+                z[i] = -INFINITY;
+                if (k < K) {
+                    float a = 0.f;
 #pragma unroll
-                        for (int q = 0; q < NS4; ++q) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                            a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
-                            a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
-                        }
-                        z[i] = a + s_b[k];
-                        sm[i] = grow[k] * inv;
-                        if (z[i] > zmax) { zmax = z[i]; zarg = k; }      // ascending k: first maximum wins
-                        if (sm[i] > smax) { smax = sm[i]; sarg = k; }
+                    for (int q = 0; q < NS4; ++q) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                        a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
+                        a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
                     }
-                }
+                    z[i] = a + s_b[k];
+                    if (z[i] > zmax) { zmax = z[i]; zarg = k; }          // ascending k: first maximum wins
+                    if (sm[i] > smax) { smax = sm[i]; sarg = k; }
+                } else sm[i] = -INFINITY;
             }
             warp_argmax(zmax, zarg);
             warp_argmax(smax, sarg);
 
-            // softmax of the logits (P'), softmax of t*sim (P) and its entropy term E = sum P log P
+            // softmax numerators, computed once: z <- exp(z - zmax), pa <- exp(t (sim - smax)); label bits
+            float pa[KI];
             float zsum = 0.f, asum = 0.f;
+            unsigned lmask = 0;
 #pragma unroll
-            for (int i = 0; i < KI_MAX; ++i)
-                if (i < KI && lane + 32 * i < K) {
-                    zsum += expf(z[i] - zmax);
-                    asum += expf(t_anneal * (sm[i] - smax));
-                }
+            for (int i = 0; i < KI; ++i) {
+                const bool ok = lane + 32 * i < K;
+                const float a = t_anneal * (sm[i] - smax);
+                lmask |= (ok && sm[i] == smax) ? (1u << i) : 0u;
+                z[i] = ok ? __expf(z[i] - zmax) : 0.f;
+                pa[i] = ok ? __expf(a) : 0.f;
+                sm[i] = a;                                       // sim itself is no longer needed: keep t (sim - smax)
+                zsum += z[i];
+                asum += pa[i];
+            }
             zsum = warp_sum(zsum);
             asum = warp_sum(asum);
-            const float zinv = 1.f / zsum, logZ = logf(asum), ainv = 1.f / asum;
+            const float zinv = 1.f / zsum, logZ = __logf(asum), ainv = 1.f / asum;
+            // E = sum P log P, lab = sum (P' - L)^2, dot = sum P' g, rec = sim[argmax z]
             float E = 0.f, lab = 0.f, dot = 0.f, rec = 0.f;
 #pragma unroll
-            for (int i = 0; i < KI_MAX; ++i)
-                if (i < KI && lane + 32 * i < K) {
-                    const int k = lane + 32 * i;
-                    const float a = t_anneal * (sm[i] - smax);
-                    const float P = expf(a) * ainv, logP = a - logZ;
+            for (int i = 0; i < KI; ++i) {
+                const int k = lane + 32 * i;
+                if (k < K) {
+                    const float P = pa[i] * ainv;
+                    const float logP = sm[i] - logZ;
                     E = fmaf(P, logP, E);
-                    const float Pz = expf(z[i] - zmax) * zinv;
-                    const float diff = Pz - (sm[i] == smax ? 1.f : 0.f);
+                    const float Pz = z[i] * zinv;
+                    const float diff = Pz - (float)((lmask >> i) & 1u);
                     lab = fmaf(diff, diff, lab);
                     dot = fmaf(Pz, cl * diff, dot);
                     if (k == zarg) rec = sm[i];
+                    z[i] = Pz; pa[i] = P; sm[i] = logP;
                 }
+            }
             E = warp_sum(E); lab = warp_sum(lab); dot = warp_sum(dot); rec = warp_sum(rec);
             if (lane == 0) {
-                l_lab += (double)lab; l_sim += (double)smax; l_ent += (double)E; l_rec += (double)rec;
+                // rec holds t (sim[k^] - smax): undo the shift and scale
+                l_lab += (double)lab; l_sim += (double)smax; l_ent += (double)E;
+                l_rec += (double)(rec / t_anneal + smax);
                 l_min = fminf(l_min, smax);
             }
 
             // gradients: dz -> staged row + dx partials; dsim (pre-scaled by 1/|gt|) overwrites G
-            float dxp[SP];
+            float dxp[DXN];
 #pragma unroll
-            for (int c = 0; c < SP; ++c) dxp[c] = 0.f;
+            for (int c = 0; c < DXN; ++c) dxp[c] = 0.f;
 #pragma unroll
-            for (int i = 0; i < KI_MAX; ++i)
-                if (i < KI) {
-                    const int k = lane + 32 * i;
-                    if (k < K) {
-                        const float a = t_anneal * (sm[i] - smax);
-                        const float P = expf(a) * ainv, logP = a - logZ;
-                        const float Pz = expf(z[i] - zmax) * zinv;
-                        const float g = cl * (Pz - (sm[i] == smax ? 1.f : 0.f));
-                        const float dz = Pz * (g - dot);
-                        dzrow[k] = dz;
-                        float ds = -ce * P * (logP - E);
-                        if (k == sarg) ds -= invN;
-                        if (k == zarg) ds -= invN;
-                        grow[k] = ds * inv;
+            for (int i = 0; i < KI; ++i) {
+                const int k = lane + 32 * i;
+                if (k < K) {
+                    const float Pz = z[i];
+                    const float dz = Pz * (cl * (Pz - (float)((lmask >> i) & 1u)) - dot);
+                    dzrow[k] = dz;
+                    float ds = -ce * pa[i] * (sm[i] - E);
+                    if (k == sarg) ds -= invN;
+                    if (k == zarg) ds -= invN;
+                    grow[k] = ds * inv;
 #pragma unroll
-                        for (int q = 0; q < NS4; ++q) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                            dxp[4 * q] = fmaf(dz, w4.x, dxp[4 * q]); dxp[4 * q + 1] = fmaf(dz, w4.y, dxp[4 * q + 1]);
-                            dxp[4 * q + 2] = fmaf(dz, w4.z, dxp[4 * q + 2]); dxp[4 * q + 3] = fmaf(dz, w4.w, dxp[4 * q + 3]);
-                        }
-                    } else if (k < KP) dzrow[k] = 0.f;
-                }
+                    for (int q = 0; q < NS4; ++q) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                        dxp[4 * q] = fmaf(dz, w4.x, dxp[4 * q]); dxp[4 * q + 1] = fmaf(dz, w4.y, dxp[4 * q + 1]);
+                        dxp[4 * q + 2] = fmaf(dz, w4.z, dxp[4 * q + 2]); dxp[4 * q + 3] = fmaf(dz, w4.w, dxp[4 * q + 3]);
+                    }
+                } else if (k < KP) dzrow[k] = 0.f;
+            }
             if (dL_dx) {
-#pragma unroll
-                for (int c = 0; c < SP; ++c) {
-                    const float v = warp_sum(dxp[c]);
-                    if (lane == (c & 31) && c < S) dL_dx[p * xs_n + c * xs_c] = v;
-                }
+                const float v = warp_transpose_sum<DXN>(dxp, lane);
+                const int c = dx_channel(lane, DXN);
+                if ((DXN == 32 || (lane & 1) == 0) && c < S) dL_dx[p * xs_n + c * xs_c] = v;
             }
         }
         __syncthreads();
         // ---------------- phase B: dW += dz^T x, db += dz over the batch ----------------
         if (dW) {
 #pragma unroll
-            for (int kk = 0; kk < KT; ++kk) {
+            for (int kk = 0; kk < KTT; ++kk) {
                 const int k = tid + ROWS_THREADS * kk;
                 if (k < K) {
                     for (int pl = 0; pl < PB; ++pl) {
@@ -317,7 +365,7 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
 
     if (dW) {
 #pragma unroll
-        for (int kk = 0; kk < KT; ++kk) {
+        for (int kk = 0; kk < KTT; ++kk) {
             const int k = tid + ROWS_THREADS * kk;
             if (k < K) {
                 if (db) atomicAdd(db + k, accb[kk]);
@@ -388,13 +436,13 @@ cublasHandle_t g_handle[64] = {nullptr};
 
 int sem_groups(int S) { return S <= 4 ? 1 : S <= 8 ? 2 : S <= 12 ? 3 : S <= 16 ? 4 : 8; }
 
-template <int NS4>
-cudaError_t launch_rows(const goi_semloss_args& a, const Workspace& w, cudaStream_t st)
+template <int NS4, int KI>
+cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, cudaStream_t st)
 {
     constexpr int SP = 4 * NS4;
     const int KP = (a.K + 31) & ~31;
     const size_t smem = sizeof(float) * ((size_t)a.K * (SP + 4) + ((a.K + 3) & ~3) + PB * SP + (size_t)PB * KP);
-    auto kern = k_semloss_rows<NS4>;
+    auto kern = k_semloss_rows<NS4, KI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
@@ -408,6 +456,15 @@ cudaError_t launch_rows(const goi_semloss_args& a, const Workspace& w, cudaStrea
                                                     w.inv_norm, a.mlp_weight, a.mlp_bias, a.dL_dx, a.dL_dmlp_weight,
                                                     a.dL_dmlp_bias, w.acc);
     return cudaGetLastError();
+}
+
+template <int NS4>
+cudaError_t launch_rows(const goi_semloss_args& a, const Workspace& w, cudaStream_t st)
+{
+    // lanes own ceil(K / 32) codebook rows: 10 covers the reference's K = 300 without wasted unrolled iterations
+    if (a.K <= 160) return launch_rows_t<NS4, 5>(a, w, st);
+    if (a.K <= 320) return launch_rows_t<NS4, 10>(a, w, st);
+    return launch_rows_t<NS4, 16>(a, w, st);
 }
 
 }  // namespace
