@@ -45,6 +45,7 @@ CONFIGS = {
     "c1": (10_000, 256, 256, 10, 0),
     "c2": (1_000_000, 1600, 1000, 16, 1),
     "c3": (1_000_000, 800, 600, 32, 2),
+    "c4": (5_000_000, 1920, 1080, 16, 3),      # BASELINE config 4: 64 views over 8 GPUs = --gpus 8 --views-per-step 8
     "c5_4": (1_000_000, 1280, 720, 4, 4), "c5_8": (1_000_000, 1280, 720, 8, 4),
     "c5_16": (1_000_000, 1280, 720, 16, 4), "c5_32": (1_000_000, 1280, 720, 32, 4),
     "c5_64": (1_000_000, 1280, 720, 64, 4),
