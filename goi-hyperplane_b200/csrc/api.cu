@@ -272,8 +272,9 @@ static int validate_mask(const goi_mask_args* a, bool standalone)
     if (a->mode != GOI_MASK_APE && a->mode != GOI_MASK_OSH) return fail(GOI_ERR_INVALID_ARG, "bad mode");
     if ((standalone && !a->x) || !a->mlp_weight || !a->lut || !a->hyperplane_w || !a->sim_table || !a->sim)
         return fail(GOI_ERR_INVALID_ARG, "null pointers");
-    const size_t smem = (size_t)a->K * sem_groups(a->S) * 16 + 2 * (size_t)a->K * 4;
-    if (smem > 200 * 1024) return fail(GOI_ERR_UNSUPPORTED, "codebook projection (K=%d, S=%d) does not fit shared memory", a->K, a->S);
+    // shared-memory image of the projection: TF32 hi + lo of [K8][4*groups + 4] + bias + sim table (goi_mask_mma.cuh)
+    const size_t smem = (size_t)((a->K + 7) & ~7) * (2 * (4 * sem_groups(a->S) + 4) + 1) * 4 + (size_t)a->K * 4;
+    if (smem > 220 * 1024) return fail(GOI_ERR_UNSUPPORTED, "codebook projection (K=%d, S=%d) does not fit shared memory", a->K, a->S);
     return GOI_OK;
 }
 

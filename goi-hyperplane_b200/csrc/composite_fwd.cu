@@ -26,6 +26,7 @@
 // per pixel = 4(S+5) + 4 written.
 #include "goi_internal.cuh"
 #include "goi_cull.cuh"
+#include "goi_mask_mma.cuh"
 
 namespace goi {
 
@@ -43,7 +44,7 @@ struct MaskEpilogue {
 };
 
 template <int NS4, int BATCH, bool TRACE, bool MASK>
-__global__ void __launch_bounds__(COMPOSITE_THREADS)
+__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 4 : 1))   // 64 registers: the mask epilogue may spill, the walk must not
 k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg,
@@ -235,36 +236,19 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         }
     }
 
-    if (MASK && NS4 > 0) {
-        // Same arithmetic as k_mask_apply (mask.cu) on the values just written to out_sem: fmaf chain over the
-        // channels in order, + bias, first maximum wins.  The staging area is dead by now (every cp.async was
-        // waited for before the last barrier) and becomes the projection table.
-        constexpr int SP = NS4 > 0 ? 4 * NS4 : 1;           // (NS4 == 0 never runs this block)
-        float4* s_w = smem;                                 // [K][NS4]
-        float* s_b = reinterpret_cast<float*>(smem + (size_t)me.K * NS4);
-        float* s_tab = s_b + me.K;
+    if constexpr (MASK && NS4 > 0) {
+        // Same routine as k_mask_apply (mask.cu) on the values just written to out_sem: bit-identical results.  The
+        // staging area is dead by now (every cp.async was waited for before the last barrier) and becomes the
+        // projection table; the 32 pixels of the warp are the rows of the tensor-core tiles.
         __syncthreads();
-        for (int i = tid; i < me.K * SP; i += COMPOSITE_THREADS) {
-            const int k = i / SP, c = i % SP;
-            reinterpret_cast<float*>(s_w)[i] = c < S ? me.mlp_w[(size_t)k * S + c] : 0.f;
-        }
-        for (int i = tid; i < me.K; i += COMPOSITE_THREADS) { s_b[i] = me.mlp_b ? me.mlp_b[i] : 0.f; s_tab[i] = me.sim_table[i]; }
+        const MaskWeights<NS4> mw = mask_stage_weights<NS4>(smem, me.K, S, me.mlp_w, me.mlp_b, tid, COMPOSITE_THREADS);
+        float* s_tab = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + MaskWeights<NS4>::bytes(me.K));
+        for (int i = tid; i < me.K; i += COMPOSITE_THREADS) s_tab[i] = me.sim_table[i];
         __syncthreads();
-        float best = -INFINITY;
-        int bi = 0;
-        for (int k = 0; k < me.K; ++k) {
-            float a = 0.f;
+        float xv[4 * NS4];
 #pragma unroll
-            for (int q = 0; q < NS4; ++q) {
-                const float4 w4 = s_w[k * NS4 + q];
-                a = fmaf(Cs[2 * q].x, w4.x, a);
-                a = fmaf(Cs[2 * q].y, w4.y, a);
-                a = fmaf(Cs[2 * q + 1].x, w4.z, a);
-                a = fmaf(Cs[2 * q + 1].y, w4.w, a);
-            }
-            const float v = a + s_b[k];
-            if (v > best) { best = v; bi = k; }
-        }
+        for (int q = 0; q < 2 * NS4; ++q) { xv[2 * q] = Cs[q].x; xv[2 * q + 1] = Cs[q].y; }
+        const int bi = warp_project_argmax<NS4>(xv, mw, lane);
         if (inside) {
             const float sv = s_tab[bi];
             const bool below = sv < me.thresh;
@@ -286,7 +270,7 @@ static cudaError_t launch_fwd_t(const goi_view& v, const goi_gaussians& g, const
     constexpr int ROW = 1 + NS4;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
     size_t smem = (size_t)3 * BATCH * (2 + ROW) * sizeof(float4);
-    if (MASK) smem = max(smem, (size_t)me.K * NS4 * sizeof(float4) + 2 * (size_t)me.K * sizeof(float));
+    if (MASK && NS4 > 0) smem = max(smem, MaskWeights<(NS4 > 0 ? NS4 : 1)>::bytes(me.K) + (size_t)me.K * sizeof(float));
     auto kern = k_composite_fwd<NS4, BATCH, TRACE, MASK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

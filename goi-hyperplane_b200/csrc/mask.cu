@@ -10,11 +10,12 @@
 //     bg   = sim < thresh;  sim[bg] = 0             gui/main.py:381-384
 // The reference materialises [N,K] logits + softmax and two [N,D] feature tensors (about 7 GB of
 // temporaries at 1.6 Mpx).  Everything after the argmax depends only on idx, so the K-entry sim table
-// is computed once (k_mask_table, K blocks) and the per-element kernel does the S->K projection in
-// registers, tracks the arg-max (first maximum wins, like torch.argmax), and does one table lookup:
-// 4S bytes in, 4 + 1 (+4) bytes out per element.  softmax(10 x) is strictly monotone in x, so its
+// is computed once (k_mask_table, K blocks) and the per-element kernel does the S->K projection on the
+// tensor cores (3xTF32 mma.sync, goi_mask_mma.cuh), tracks the arg-max (first maximum wins, like torch.argmax),
+// and does one table lookup: 4S bytes in, 4 + 1 (+4) bytes out per element.  softmax(10 x) is strictly monotone in x, so its
 // argmax is the argmax of the logits (ties at float resolution are the documented exception).
 #include "goi_internal.cuh"
+#include "goi_mask_mma.cuh"
 
 namespace goi {
 
@@ -49,92 +50,60 @@ __global__ void __launch_bounds__(128) k_mask_table(int K, int D, int mode, cons
     }
 }
 
-template <int NS4, int PPT>
-__global__ void __launch_bounds__(256) k_mask_apply(int64_t N, int S, int K, int64_t stride_n, int64_t stride_c,
-                                                    const float* __restrict__ x, const float* __restrict__ mlp_w,
-                                                    const float* __restrict__ mlp_b,
-                                                    const float* __restrict__ sim_table, float thresh,
-                                                    float* __restrict__ sim, uint8_t* __restrict__ bg_mask,
-                                                    int32_t* __restrict__ idx_out)
+// One warp = 32 consecutive elements per iteration; the S -> K projection + arg-max runs on the tensor cores
+// (goi_mask_mma.cuh), everything after the arg-max is one lookup in the K-entry sim table.
+template <int NS4, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_mask_apply(int64_t N, int S, int K, int64_t stride_n, int64_t stride_c,
+                                                        const float* __restrict__ x, const float* __restrict__ mlp_w,
+                                                        const float* __restrict__ mlp_b,
+                                                        const float* __restrict__ sim_table, float thresh,
+                                                        float* __restrict__ sim, uint8_t* __restrict__ bg_mask,
+                                                        int32_t* __restrict__ idx_out)
 {
     constexpr int SP = 4 * NS4;                         // padded channel count
     extern __shared__ float4 smem_m[];
-    float4* s_w = smem_m;                               // [K][NS4]
-    float* s_b = reinterpret_cast<float*>(smem_m + (size_t)K * NS4);   // [K]
-    float* s_tab = s_b + K;                             // [K]
-    for (int i = threadIdx.x; i < K * SP; i += blockDim.x) {
-        const int k = i / SP, c = i % SP;
-        reinterpret_cast<float*>(s_w)[i] = c < S ? mlp_w[(size_t)k * S + c] : 0.f;
-    }
-    for (int i = threadIdx.x; i < K; i += blockDim.x) { s_b[i] = mlp_b ? mlp_b[i] : 0.f; s_tab[i] = sim_table[i]; }
+    const MaskWeights<NS4> mw = mask_stage_weights<NS4>(smem_m, K, S, mlp_w, mlp_b, threadIdx.x, THREADS);
+    float* s_tab = reinterpret_cast<float*>(reinterpret_cast<char*>(smem_m) + MaskWeights<NS4>::bytes(K));   // [K]
+    for (int i = threadIdx.x; i < K; i += THREADS) s_tab[i] = sim_table[i];
     __syncthreads();
 
-    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x) * PPT; base < N; base += (int64_t)gridDim.x * blockDim.x * PPT) {
-        float xv[PPT][SP];
-        int64_t nidx[PPT];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
+    for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {       // warp-uniform trip count
+        const int64_t n = base + lane;                  // consecutive lanes -> consecutive elements
+        float xv[SP];
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            nidx[p] = base + (int64_t)p * blockDim.x + threadIdx.x;   // consecutive threads -> consecutive elements
-#pragma unroll
-            for (int c = 0; c < SP; ++c)
-                xv[p][c] = (c < S && nidx[p] < N) ? x[nidx[p] * stride_n + c * stride_c] : 0.f;
-        }
-        float best[PPT];
-        int bi[PPT];
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) { best[p] = -INFINITY; bi[p] = 0; }
-        for (int k = 0; k < K; ++k) {
-            float a[PPT];
-#pragma unroll
-            for (int p = 0; p < PPT; ++p) a[p] = 0.f;
-#pragma unroll
-            for (int q = 0; q < NS4; ++q) {
-                const float4 w4 = s_w[k * NS4 + q];
-#pragma unroll
-                for (int p = 0; p < PPT; ++p) {
-                    a[p] = fmaf(xv[p][4 * q + 0], w4.x, a[p]);
-                    a[p] = fmaf(xv[p][4 * q + 1], w4.y, a[p]);
-                    a[p] = fmaf(xv[p][4 * q + 2], w4.z, a[p]);
-                    a[p] = fmaf(xv[p][4 * q + 3], w4.w, a[p]);
-                }
-            }
-            const float bk = s_b[k];
-#pragma unroll
-            for (int p = 0; p < PPT; ++p) {
-                const float v = a[p] + bk;
-                if (v > best[p]) { best[p] = v; bi[p] = k; }
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            if (nidx[p] < N) {
-                const float s = s_tab[bi[p]];
-                const bool bg = s < thresh;
-                sim[nidx[p]] = bg ? 0.f : s;
-                if (bg_mask) bg_mask[nidx[p]] = bg ? 1 : 0;
-                if (idx_out) idx_out[nidx[p]] = bi[p];
-            }
+        for (int c = 0; c < SP; ++c) xv[c] = (c < S && n < N) ? x[n * stride_n + c * stride_c] : 0.f;
+        const int bi = warp_project_argmax<NS4>(xv, mw, lane);
+        if (n < N) {
+            const float sv = s_tab[bi];
+            const bool bg = sv < thresh;
+            sim[n] = bg ? 0.f : sv;
+            if (bg_mask) bg_mask[n] = bg ? 1 : 0;
+            if (idx_out) idx_out[n] = bi;
         }
     }
 }
 
-template <int NS4, int PPT>
+template <int NS4, int THREADS>
 static cudaError_t launch_mask_t(const goi_mask_args& a, cudaStream_t st)
 {
-    auto kern = k_mask_apply<NS4, PPT>;
-    const size_t smem = (size_t)a.K * NS4 * sizeof(float4) + 2 * (size_t)a.K * sizeof(float);
+    auto kern = k_mask_apply<NS4, THREADS>;
+    const size_t smem = MaskWeights<NS4>::bytes(a.K) + (size_t)a.K * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t per_block = 256 * PPT;
+    const int64_t per_block = THREADS;
     int64_t blocks = (a.N + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)sms * 8;              // grid-stride: a few resident CTAs per SM
+    const int resident = smem > 100 * 1024 ? 1 : smem > 70 * 1024 ? 2 : 3;   // CTAs that fit one SM's shared memory
+    const int64_t cap = (int64_t)sms * resident;       // persistent grid-stride: the projection is staged once per CTA
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(a.N, a.S, a.K, a.stride_n, a.stride_c, a.x, a.mlp_weight, a.mlp_bias,
-                                              a.sim_table, a.thresh, a.sim, a.bg_mask, a.idx);
+    kern<<<(unsigned)blocks, THREADS, smem, st>>>(a.N, a.S, a.K, a.stride_n, a.stride_c, a.x, a.mlp_weight, a.mlp_bias,
+                                                  a.sim_table, a.thresh, a.sim, a.bg_mask, a.idx);
     count_launches(1);
     return cudaGetLastError();
 }
@@ -182,12 +151,12 @@ cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
     if (a.N <= 0) return cudaSuccess;
     switch (sem_groups(a.S)) {
         case 0: return cudaErrorInvalidValue;
-        case 1: return launch_mask_t<1, 4>(a, st);
-        case 2: return launch_mask_t<2, 4>(a, st);
-        case 3: return launch_mask_t<3, 2>(a, st);
-        case 4: return launch_mask_t<4, 2>(a, st);
-        case 8: return launch_mask_t<8, 1>(a, st);
-        default: return launch_mask_t<16, 1>(a, st);
+        case 1: return launch_mask_t<1, 256>(a, st);
+        case 2: return launch_mask_t<2, 256>(a, st);
+        case 3: return launch_mask_t<3, 256>(a, st);
+        case 4: return launch_mask_t<4, 256>(a, st);
+        case 8: return launch_mask_t<8, 256>(a, st);
+        default: return launch_mask_t<16, 256>(a, st);
     }
 }
 
