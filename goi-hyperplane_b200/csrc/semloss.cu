@@ -173,18 +173,21 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
     constexpr int DXN = SP <= 16 ? 16 : 32;     // dx reduction width
     constexpr int PPW = PB / 8;                 // pixels per warp per batch
     extern __shared__ float4 smem4[];
-    float* s_w = reinterpret_cast<float*>(smem4);               // [K][WS]
-    float* s_b = s_w + (size_t)K * WS;                          // [K]
-    float* s_x = s_b + ((K + 3) & ~3);                          // [PB][SP]
+    // Codebook rows are padded to KP = 32 KI with zero weights and a bias of -inf: a padded row has logit -inf,
+    // softmax weight 0 and gradient 0, so the per-lane loops below run without any k < K control flow (the guards
+    // cost more issue slots than the arithmetic they protected in the r01f capture).
+    constexpr int KP = 32 * KI;
+    float* s_w = reinterpret_cast<float*>(smem4);               // [KP][WS]
+    float* s_b = s_w + (size_t)KP * WS;                         // [KP]
+    float* s_x = s_b + KP;                                      // [PB][SP]
     float* s_dz = s_x + PB * SP;                                // [PB][KP]
-    const int KP = (K + 31) & ~31;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < K * SP; i += ROWS_THREADS) {
+    for (int i = tid; i < KP * SP; i += ROWS_THREADS) {
         const int k = i / SP, c = i % SP;
-        s_w[k * WS + c] = c < S ? W[(size_t)k * S + c] : 0.f;
+        s_w[k * WS + c] = (k < K && c < S) ? W[(size_t)k * S + c] : 0.f;
     }
-    for (int i = tid; i < K; i += ROWS_THREADS) s_b[i] = bias ? bias[i] : 0.f;
+    for (int i = tid; i < KP; i += ROWS_THREADS) s_b[i] = i < K ? (bias ? bias[i] : 0.f) : -INFINITY;
     __syncthreads();
 
     const float invN = 1.0f / (float)N;
@@ -229,11 +232,11 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
                 continue;
             }
             for (int c = lane; c < SP; c += 32) xrow[c] = c < S ? x[p * xs_n + c * xs_c] : 0.f;
-            // this pixel's prefetched row -> sim, then start the next pixel's loads
+            // this pixel's prefetched row -> sim (padded rows: -inf), then start the next pixel's loads
             float sm[KI];
             const float inv = invn;
 #pragma unroll
-            for (int i = 0; i < KI; ++i) sm[i] = gn[i] * inv;
+            for (int i = 0; i < KI; ++i) sm[i] = (lane + 32 * i < K) ? gn[i] * inv : -INFINITY;
             prefetch(pnext);
             __syncwarp();
             float xs[SP];
@@ -251,19 +254,17 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
                 const int k = lane + 32 * i;
-                z[i] = -INFINITY;
-                if (k < K) {
-                    float a = 0.f;
+                float a = 0.f;
 #pragma unroll
-                    for (int q = 0; q < NS4; ++q) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                        a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
-                        a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
-                    }
-                    z[i] = a + s_b[k];
-                    if (z[i] > zmax) { zmax = z[i]; zarg = k; }          // ascending k: first maximum wins
-                    if (sm[i] > smax) { smax = sm[i]; sarg = k; }
-                } else sm[i] = -INFINITY;
+                for (int q = 0; q < NS4; ++q) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                    a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
+                    a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
+                }
+                z[i] = a + s_b[k];
+                if (z[i] > zmax) { zmax = z[i]; zarg = k; }              // ascending k: first maximum wins
+                if (sm[i] > smax) { smax = sm[i]; sarg = k; }
+                asm volatile("" ::: "memory");                   // keep the weight loads of later rows from piling up in registers
             }
             warp_argmax(zmax, zarg);
             warp_argmax(smax, sarg);
@@ -274,11 +275,10 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
             unsigned lmask = 0;
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
-                const bool ok = lane + 32 * i < K;
                 const float a = t_anneal * (sm[i] - smax);
-                lmask |= (ok && sm[i] == smax) ? (1u << i) : 0u;
-                z[i] = ok ? __expf(z[i] - zmax) : 0.f;
-                pa[i] = ok ? __expf(a) : 0.f;
+                lmask |= (sm[i] == smax) ? (1u << i) : 0u;
+                z[i] = __expf(z[i] - zmax);                      // padded rows: exp(-inf) = 0
+                pa[i] = __expf(a);
                 sm[i] = a;                                       // sim itself is no longer needed: keep t (sim - smax)
                 zsum += z[i];
                 asum += pa[i];
@@ -286,22 +286,20 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
             zsum = warp_sum(zsum);
             asum = warp_sum(asum);
             const float zinv = 1.f / zsum, logZ = __logf(asum), ainv = 1.f / asum;
-            // E = sum P log P, lab = sum (P' - L)^2, dot = sum P' g, rec = sim[argmax z]
+            // E = sum P log P, lab = sum (P' - L)^2, dot = sum P' g, rec = t (sim[argmax z] - smax)
             float E = 0.f, lab = 0.f, dot = 0.f, rec = 0.f;
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
                 const int k = lane + 32 * i;
-                if (k < K) {
-                    const float P = pa[i] * ainv;
-                    const float logP = sm[i] - logZ;
-                    E = fmaf(P, logP, E);
-                    const float Pz = z[i] * zinv;
-                    const float diff = Pz - (float)((lmask >> i) & 1u);
-                    lab = fmaf(diff, diff, lab);
-                    dot = fmaf(Pz, cl * diff, dot);
-                    if (k == zarg) rec = sm[i];
-                    z[i] = Pz; pa[i] = P; sm[i] = logP;
-                }
+                const float P = pa[i] * ainv;
+                const float logP = (k < K) ? sm[i] - logZ : 0.f;       // (0 * -inf of a padded row would be NaN)
+                E = fmaf(P, logP, E);
+                const float Pz = z[i] * zinv;
+                const float diff = Pz - ((lmask & (1u << i)) ? 1.f : 0.f);
+                lab = fmaf(diff, diff, lab);
+                dot = fmaf(Pz, cl * diff, dot);
+                rec = (k == zarg) ? sm[i] : rec;
+                z[i] = Pz; pa[i] = P; sm[i] = logP;
             }
             E = warp_sum(E); lab = warp_sum(lab); dot = warp_sum(dot); rec = warp_sum(rec);
             if (lane == 0) {
@@ -318,21 +316,20 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
                 const int k = lane + 32 * i;
-                if (k < K) {
-                    const float Pz = z[i];
-                    const float dz = Pz * (cl * (Pz - (float)((lmask >> i) & 1u)) - dot);
-                    dzrow[k] = dz;
-                    float ds = -ce * pa[i] * (sm[i] - E);
-                    if (k == sarg) ds -= invN;
-                    if (k == zarg) ds -= invN;
-                    grow[k] = ds * inv;
+                const float Pz = z[i];
+                const float dz = Pz * (cl * (Pz - ((lmask & (1u << i)) ? 1.f : 0.f)) - dot);   // 0 for padded rows
+                dzrow[k] = dz;
+                float ds = -ce * pa[i] * (sm[i] - E);
+                ds -= (k == sarg) ? invN : 0.f;
+                ds -= (k == zarg) ? invN : 0.f;
+                if (k < K) grow[k] = ds * inv;
 #pragma unroll
-                    for (int q = 0; q < NS4; ++q) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                        dxp[4 * q] = fmaf(dz, w4.x, dxp[4 * q]); dxp[4 * q + 1] = fmaf(dz, w4.y, dxp[4 * q + 1]);
-                        dxp[4 * q + 2] = fmaf(dz, w4.z, dxp[4 * q + 2]); dxp[4 * q + 3] = fmaf(dz, w4.w, dxp[4 * q + 3]);
-                    }
-                } else if (k < KP) dzrow[k] = 0.f;
+                for (int q = 0; q < NS4; ++q) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                    dxp[4 * q] = fmaf(dz, w4.x, dxp[4 * q]); dxp[4 * q + 1] = fmaf(dz, w4.y, dxp[4 * q + 1]);
+                    dxp[4 * q + 2] = fmaf(dz, w4.z, dxp[4 * q + 2]); dxp[4 * q + 3] = fmaf(dz, w4.w, dxp[4 * q + 3]);
+                }
+                asm volatile("" ::: "memory");
             }
             if (dL_dx) {
                 const float v = warp_transpose_sum<DXN>(dxp, lane);
@@ -440,8 +437,8 @@ template <int NS4, int KI>
 cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, cudaStream_t st)
 {
     constexpr int SP = 4 * NS4;
-    const int KP = (a.K + 31) & ~31;
-    const size_t smem = sizeof(float) * ((size_t)a.K * (SP + 4) + ((a.K + 3) & ~3) + PB * SP + (size_t)PB * KP);
+    constexpr int KP = 32 * KI;                                 // padded codebook rows (see the kernel)
+    const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + PB * SP + (size_t)PB * KP);
     auto kern = k_semloss_rows<NS4, KI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
