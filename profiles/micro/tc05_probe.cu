@@ -3,7 +3,7 @@
 //     element (row r, k) at  (r / 8) * SBO + (k / 4) * LBO + (r % 8) * 16 + (k % 4) * 4   bytes,
 //     LBO = 128 (the two 16-byte K chunks of one MMA k-step are 128 B apart), SBO = (K / 4) * 128.
 // Verifies the descriptor encodings (cute/arch/mma_sm100_desc.hpp) and the TMEM read-back against the CPU.
-// Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tc05_probe tc05_probe.cu
+// Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o /tmp/tc05_probe profiles/micro/tc05_probe.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
