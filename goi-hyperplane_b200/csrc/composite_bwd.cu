@@ -42,7 +42,7 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp: x =
 }
 
 template <int NS4, int BATCH>
-__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 3 : 1))
+__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 3 : NS4 <= 8 ? 2 : 1))
 k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                 const uint32_t* __restrict__ cull, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,

@@ -44,7 +44,7 @@ struct MaskEpilogue {
 };
 
 template <int NS4, int BATCH, bool TRACE, bool MASK>
-__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 4 : 1))   // 64 registers: the mask epilogue may spill, the walk must not
+__global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 4 : NS4 <= 8 ? 3 : 1))   // 64 registers: the mask epilogue may spill, the walk must not
 k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg,
