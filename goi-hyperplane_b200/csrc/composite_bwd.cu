@@ -66,11 +66,11 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     float4* s_g0 = smem;                               // [2][BATCH]
     float4* s_g1 = smem + 2 * BATCH;                   // [2][BATCH]
     float4* s_pay = smem + 4 * BATCH;                  // [2][BATCH][ROW]
-    float* s_red = reinterpret_cast<float*>(smem + 4 * BATCH + 2 * BATCH * ROW);   // [8 warps][2][DROWS][RSTRIDE]
+    float* s_red = reinterpret_cast<float*>(smem + 4 * BATCH + 2 * BATCH * ROW);   // [8 warps][DROWS][RSTRIDE]
     // second stage of the reduction: [8 warps][4 value groups][VS], value u of pixel group pg at u*USTRIDE + pg
     constexpr int USTRIDE = 12;                        // floats between values: 16-B aligned, LDS.128 conflict-free
     constexpr int VS = NBLK * 8 * USTRIDE + 8;         // floats per value group: (VS mod 32 == 8) keeps the STS conflict-free
-    float* s_tr = s_red + 8 * 2 * DROWS * RSTRIDE;
+    float* s_tr = s_red + 8 * DROWS * RSTRIDE;
     __shared__ uint32_t s_max_contrib;
     __shared__ uint32_t s_cull[2][BATCH];              // the forward's warp-block masks of the staged instances
 
@@ -119,7 +119,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     float2 gp[NP2 > 0 ? NP2 : 1][4];
     float gtail[4] = {0.f, 0.f, 0.f, 0.f};
     {
-        float* gt = s_red + warp * (2 * DROWS * RSTRIDE);       // scratch: one value row at a time, reuse dyn rows
+        float* gt = s_red + warp * (DROWS * RSTRIDE);           // scratch: one value row at a time, reuse dyn rows
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < PPG; ++u) {
@@ -218,19 +218,18 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 
     float last_alpha = 0.f, last_q = 0.f, acc = 0.f;
     const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
-    // Shared-memory addresses of the per-warp reduction rows, kept in four registers (laundered through an
-    // opaque mov so the compiler does not re-derive them from %tid inside the walk):
-    //   ad      this walk's publish address (row 0, this lane's column); alternates between the two halves
-    //   ad_sum  sum of both halves' publish addresses (ad <- ad_sum - ad flips the half)
+    // Shared-memory addresses of the per-warp reduction rows, kept in registers (laundered through an opaque mov
+    // so the compiler does not re-derive them from %tid inside the walk).  The rows are single-buffered: a lane
+    // can only reach the next walk's stores after the second __syncwarp of this walk, i.e. after every lane has
+    // read the rows.
+    //   ad      publish address (row 0, this lane's column)
     //   dl      ad + dl = this lane's 4-pixel group in row 0 (pg * 16 - lane * 4)
     //   go      byte offset of the first of this value group's two geometry rows (rows 1+2vg, 2+2vg); the
     //           fourth group has none and reads rows 0/1 into values that are never written out
-    const uint32_t a_dyn = smem_u32(s_red + warp * (2 * DROWS * RSTRIDE));
-    uint32_t ad = a_dyn + lane * 4 + DROWS * RSTRIDE * 4;
-    uint32_t ad_sum = 2 * (a_dyn + lane * 4) + DROWS * RSTRIDE * 4;
+    uint32_t ad = smem_u32(s_red + warp * (DROWS * RSTRIDE)) + lane * 4;
     uint32_t dl = (uint32_t)(pg * 16 - lane * 4);
     uint32_t go = vg < 3 ? (uint32_t)((1 + 2 * vg) * RSTRIDE * 4) : 0u;
-    asm volatile("mov.u32 %0, %0;" : "+r"(ad_sum));
+    asm volatile("mov.u32 %0, %0;" : "+r"(ad));
     asm volatile("mov.u32 %0, %0;" : "+r"(dl));
     asm volatile("mov.u32 %0, %0;" : "+r"(go));
     //   atw     this lane's column pg of value 0 in its value group of the transpose region; atr: value pg's row
@@ -306,7 +305,6 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
                 const float dG_ddely = -gdy * g1.x - gdx * g0.w;
                 const float hx = -0.5f * gdx * dL_dG, hy = -0.5f * gdy * dL_dG;
-                ad = ad_sum - ad;                           // other half of the double-buffered rows
                 sts32(ad + 0 * RSTRIDE * 4, a_eff * T);
                 sts32(ad + 1 * RSTRIDE * 4, dL_dG * dG_ddelx);
                 sts32(ad + 2 * RSTRIDE * 4, dL_dG * dG_ddely);
@@ -366,7 +364,7 @@ static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const
     constexpr int ROW = 1 + NS4;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
     constexpr int NBLK = ((4 + 4 * NS4 + 3) / 4 + 2 + 7) / 8;
-    const size_t smem = (size_t)2 * BATCH * (2 + ROW) * sizeof(float4) + (size_t)(8 * 2 * 7) * RSTRIDE * sizeof(float) +
+    const size_t smem = (size_t)2 * BATCH * (2 + ROW) * sizeof(float4) + (size_t)(8 * 7) * RSTRIDE * sizeof(float) +
                         (size_t)8 * 4 * (NBLK * 8 * 12 + 8) * sizeof(float);
     auto kern = k_composite_bwd<NS4, BATCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
