@@ -74,7 +74,11 @@ cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st)
                            cudaMemcpyDeviceToDevice, st);
 }
 
-// One thread per depth rank; emits that Gaussian's surviving tiles row-major (the reference's loop nest).
+// One thread per depth rank; emits that Gaussian's surviving tiles row-major (the reference's loop nest).  Rectangles
+// of more than kCoopTiles tiles are emitted by the whole warp, 32 tiles per step with a ballot prefix for the output
+// slots (same test, same row-major order), so a handful of very large splats cannot stall the kernel.
+constexpr int kCoopTiles = 32;      // must match preprocess.cu (only a work split: both paths run the same test)
+
 __global__ void __launch_bounds__(256) k_emit_keys(int P, const uint32_t* __restrict__ order,
                                                    const float4* __restrict__ geo,
                                                    const uint32_t* __restrict__ offsets,
@@ -82,22 +86,56 @@ __global__ void __launch_bounds__(256) k_emit_keys(int P, const uint32_t* __rest
                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= P) return;
-    uint32_t off = (k == 0) ? 0 : offsets[k - 1];
-    const uint32_t end = offsets[k];
-    if (off == end) return;                   // culled, or no tile survives the exact test
-    const uint32_t idx = order[k];
-    const uint2 rc = rect[idx];
-    const uint32_t minx = rc.x & 0xffffu, miny = rc.x >> 16, maxx = rc.y & 0xffffu, maxy = rc.y >> 16;
-    const float4 g0 = geo[2 * (size_t)idx], g1 = geo[2 * (size_t)idx + 1];
-    for (uint32_t y = miny; y < maxy; ++y)
-        for (uint32_t x = minx; x < maxx; ++x) {
-            if (!tile_may_contribute(g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, (int)x, (int)y, W, H)) continue;
-            if (off >= end) return;           // cannot happen (same bit-exact test as the count); never overrun
-            keys[off] = y * (uint32_t)gx + x;
-            vals[off] = idx;
-            ++off;
-        }
+    const int lane = threadIdx.x & 31;
+    uint32_t off = 0, end = 0, idx = 0;
+    uint32_t minx = 0, miny = 0, maxx = 0, maxy = 0;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    if (k < P) {
+        off = (k == 0) ? 0 : offsets[k - 1];
+        end = offsets[k];
+    }
+    const bool active = off != end;           // otherwise culled, or no tile survives the exact test
+    if (active) {
+        idx = order[k];
+        const uint2 rc = rect[idx];
+        minx = rc.x & 0xffffu; miny = rc.x >> 16; maxx = rc.y & 0xffffu; maxy = rc.y >> 16;
+        g0 = geo[2 * (size_t)idx]; g1 = geo[2 * (size_t)idx + 1];
+    }
+    const uint32_t area = (maxx - minx) * (maxy - miny);
+    if (active && area <= (uint32_t)kCoopTiles) {
+        for (uint32_t y = miny; y < maxy; ++y)
+            for (uint32_t x = minx; x < maxx; ++x) {
+                if (!tile_may_contribute(g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, (int)x, (int)y, W, H)) continue;
+                if (off >= end) break;        // cannot happen (same bit-exact test as the count); never overrun
+                keys[off] = y * (uint32_t)gx + x;
+                vals[off] = idx;
+                ++off;
+            }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, active && area > (uint32_t)kCoopTiles);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const float mx = __shfl_sync(0xffffffffu, g0.x, src), my = __shfl_sync(0xffffffffu, g0.y, src);
+        const float ca = __shfl_sync(0xffffffffu, g0.z, src), cb = __shfl_sync(0xffffffffu, g0.w, src);
+        const float cc = __shfl_sync(0xffffffffu, g1.x, src), pc = __shfl_sync(0xffffffffu, g1.z, src);
+        const uint32_t x0 = __shfl_sync(0xffffffffu, minx, src), x1 = __shfl_sync(0xffffffffu, maxx, src);
+        const uint32_t y0 = __shfl_sync(0xffffffffu, miny, src), y1 = __shfl_sync(0xffffffffu, maxy, src);
+        const uint32_t id = __shfl_sync(0xffffffffu, idx, src), e = __shfl_sync(0xffffffffu, end, src);
+        uint32_t o = __shfl_sync(0xffffffffu, off, src);
+        for (uint32_t y = y0; y < y1; ++y)
+            for (uint32_t xb = x0; xb < x1; xb += 32) {
+                const uint32_t x = xb + lane;
+                const bool f = x < x1 && tile_may_contribute(mx, my, ca, cb, cc, pc, (int)x, (int)y, W, H);
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const uint32_t slot = o + __popc(m & ((1u << lane) - 1u));
+                if (f && slot < e) {
+                    keys[slot] = y * (uint32_t)gx + x;
+                    vals[slot] = id;
+                }
+                o += __popc(m);
+            }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint32_t* __restrict__ keys,

@@ -263,6 +263,8 @@ __device__ __forceinline__ float4 load_rotation(const float* __restrict__ rotati
     return q;
 }
 
+constexpr int kCoopTiles = 32;      // tile rectangles larger than this are walked by a whole warp (count: k_count_big_rects, emission: binning.cu)
+
 __global__ void __launch_bounds__(128) k_preprocess_fwd(
     int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int gx, int gy, int prefiltered,
     int32_t* __restrict__ radii, float4* __restrict__ geo, float4* __restrict__ rgbd, float* __restrict__ cov3Ds,
     uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rect,
-    uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ order, Meta* meta)
+    uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ order, uint32_t* __restrict__ big_queue, Meta* meta)
 {
     // One warp = 32 consecutive Gaussians.  The per-Gaussian geometry is computed first; the SH rows of the
     // whole warp (32 x 3M contiguous floats) are then staged through shared memory with coalesced loads,
@@ -401,28 +403,68 @@ __global__ void __launch_bounds__(128) k_preprocess_fwd(
     } else if (visible) {
         rgb = make_float3(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]);
     }
-    if (!visible) return;
+    float opacity = 0.f, power_cut = 1.0f;
+    if (visible) {
+        opacity = opacities[idx];
+        if (raw_flags & GOI_RAW_OPACITY) opacity = 1.0f / (1.0f + expf(-opacity));
+        // power_cut: a pair with power < power_cut has opacity*exp(power) < 1/255 with margin, so the
+        // composite may skip it before evaluating expf (a provably non-contributing pair, never a
+        // borderline one: the margin of 0.01 in the exponent is ~1e5 ulp of the decision value).
+        power_cut = (opacity > 0.f) ? -(logf(255.f * opacity) + 0.01f) : 1.0f;
 
-    float opacity = opacities[idx];
-    if (raw_flags & GOI_RAW_OPACITY) opacity = 1.0f / (1.0f + expf(-opacity));
-    // power_cut: a pair with power < power_cut has opacity*exp(power) < 1/255 with margin, so the
-    // composite may skip it before evaluating expf (a provably non-contributing pair, never a
-    // borderline one: the margin of 0.01 in the exponent is ~1e5 ulp of the decision value).
-    const float power_cut = (opacity > 0.f) ? -(logf(255.f * opacity) + 0.01f) : 1.0f;
-
-    radii[idx] = max_radius;
-    geo[2 * idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-    geo[2 * idx + 1] = make_float4(conic.z, opacity, power_cut, __int_as_float(idx));
-    rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, depth);
-    rect[idx] = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
+        radii[idx] = max_radius;
+        geo[2 * idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+        geo[2 * idx + 1] = make_float4(conic.z, opacity, power_cut, __int_as_float(idx));
+        rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, depth);
+        rect[idx] = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
+    }
     // Instances = tiles of the reference rectangle that can actually reach alpha >= 1/255 (goi_cull.cuh).
-    // k_emit_keys repeats exactly this test, so the prefix sum and the emission agree.
-    uint32_t touched = 0;
-    for (int ty = miny; ty < maxy; ++ty)
-        for (int tx = minx; tx < maxx; ++tx)
-            touched += tile_may_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, power_cut, tx, ty, W, H) ? 1u : 0u;
-    tiles_touched[idx] = touched;
-    if (touched) depth_keys[idx] = __float_as_uint(depth);
+    // k_emit_keys repeats exactly this test, so the prefix sum and the emission agree.  Small rectangles are
+    // counted here by their own thread.  A rectangle of more than kCoopTiles tiles (real scenes have a heavy tail
+    // of large splats: such a thread would loop over thousands of tiles while its warp idles, and neighbours in
+    // memory tend to be large together) is queued for k_count_big_rects, one warp per splat across the whole GPU.
+    if (visible) {
+        const int area = (maxx - minx) * (maxy - miny);
+        if (area <= kCoopTiles) {
+            uint32_t touched = 0;
+            for (int ty = miny; ty < maxy; ++ty)
+                for (int tx = minx; tx < maxx; ++tx)
+                    touched += tile_may_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, power_cut, tx, ty, W, H) ? 1u : 0u;
+            tiles_touched[idx] = touched;
+            if (touched) depth_keys[idx] = __float_as_uint(depth);
+        } else {
+            big_queue[atomicAdd(&meta->reserved[0], 1u)] = (uint32_t)idx;      // tiles_touched stays 0 until counted
+        }
+    }
+}
+
+// One warp per queued large splat: count the tiles of its rectangle that can contribute, 32 tiles per step, with the
+// same test (same stored operands) as the per-thread path and as k_emit_keys.
+__global__ void __launch_bounds__(256) k_count_big_rects(const uint32_t* __restrict__ big_queue, const Meta* __restrict__ meta,
+                                                         const float4* __restrict__ geo, const float4* __restrict__ rgbd,
+                                                         const uint2* __restrict__ rect, int W, int H,
+                                                         uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_keys)
+{
+    const uint32_t n = meta->reserved[0];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += warps) {
+        const uint32_t idx = big_queue[q];
+        const float4 g0 = geo[2 * (size_t)idx], g1 = geo[2 * (size_t)idx + 1];
+        const uint2 rc = rect[idx];
+        const int x0 = rc.x & 0xffffu, y0 = rc.x >> 16, x1 = rc.y & 0xffffu, y1 = rc.y >> 16;
+        uint32_t cnt = 0;
+        for (int ty = y0; ty < y1; ++ty)
+            for (int tx0 = x0; tx0 < x1; tx0 += 32) {
+                const int tx = tx0 + lane;
+                const bool f = tx < x1 && tile_may_contribute(g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, tx, ty, W, H);
+                cnt += __popc(__ballot_sync(0xffffffffu, f));
+            }
+        if (lane == 0) {
+            tiles_touched[idx] = cnt;
+            if (cnt) depth_keys[idx] = __float_as_uint(rgbd[idx].w);      // view depth, stored next to the colour
+        }
+    }
 }
 
 cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int32_t* radii, const GeomState& gs,
@@ -437,8 +479,14 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
         P, v.sh_degree, g.M, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
         g.shs_rest, g.raw_flags, g.cov3D_precomp, g.colors_precomp, v.viewmatrix, v.projmatrix, v.cam_pos, v.width, v.height,
         v.tan_fovx, v.tan_fovy, focal_x, focal_y, gx, gy, v.prefiltered, radii, gs.geo, gs.rgbd, gs.cov3D,
-        gs.clamped, gs.tiles_touched, gs.rect, gs.depth_keys[0], gs.order[0], gs.meta);
-    count_launches(1);
+        gs.clamped, gs.tiles_touched, gs.rect, gs.depth_keys[0], gs.order[0], gs.order[1], gs.meta);
+    // large splats queued by the kernel above (order[1] is free until the depth sort); exits at once when none
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    k_count_big_rects<<<sms * 2, 256, 0, st>>>(gs.order[1], gs.meta, gs.geo, gs.rgbd, gs.rect, v.width, v.height,
+                                               gs.tiles_touched, gs.depth_keys[0]);
+    count_launches(2);
     return cudaGetLastError();
 }
 

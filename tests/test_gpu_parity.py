@@ -82,6 +82,32 @@ def test_cuda_matches_reference_cuda(P, W, H, S, seed):
     print("\n", rep, "\n", grep)
 
 
+@pytest.mark.parametrize("n_big,factor", [(64, 30.0), (500, 8.0), (5, 400.0)])
+def test_large_splats_match_reference_cuda(n_big, factor):
+    """Splats whose tile rectangle exceeds 32 tiles take the warp-cooperative paths (k_count_big_rects,
+    cooperative emission): images, gradients and radii must still equal the reference kernels', and two
+    runs must agree on the instance count (count and emission use the same test)."""
+    S, P, W, H, seed = 16, 30_000, 500, 333, 7
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    with torch.no_grad():
+        g._scaling[:n_big] *= factor                 # consecutive indices: the worst case for a per-thread loop
+        g._opacity[:n_big] = g._opacity[:n_big] * 0.1 + 0.01
+    bg = torch.tensor([0.2, 0.1, 0.4])
+    w = make_loss_weights(S, W, H, seed)
+    ref = run_reference_cuda(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert torch.equal(cu["radii"].cpu(), ref["radii"].cpu())
+    assert int((cu["radii"] > 64).sum()) >= min(n_big, 5) // 2      # the large ones are really on screen
+    assert_images_close(cu, ref, max_bad_frac=0.0, what="large splats vs reference cuda")
+    assert_grads_close(cu["grads"], ref["grads"], what="large splats vs reference cuda")
+    from diff_gaussian_rasterization import _C
+    r1 = _C.last_num_rendered
+    run_cuda(g, cam, bg)
+    assert _C.last_num_rendered == r1
+
+
 @pytest.mark.parametrize("P,W,H,S,seed", [(10_000, 256, 256, 10, 0), (8_000, 250, 197, 16, 3)])
 def test_oracle_pinned_by_reference_cuda(P, W, H, S, seed):
     """The CPU oracle itself is checked against the real reference kernels (parity pin)."""
