@@ -20,12 +20,16 @@
 //      weight w(p) and its six geometry-gradient values (7 STS).  The lanes are then re-indexed as
 //      (pixel group pg = lane & 7, value group vg = lane >> 3): a lane reads the four weights of its pixel
 //      group (one LDS.128), multiplies them with its register-resident 4 x PPG block of the warp's
-//      pixel-gradient matrix, and an 8-lane transposing butterfly (7 shuffles) finishes the sum, leaving
-//      one output value per lane -> one red.global.add per value per (warp, instance).  ~70 instructions
-//      and ~25 shared-memory wavefronts where a full shuffle reduction needs ~125 / 31.
+//      pixel-gradient matrix (FFMA2, the weight as broadcast operand), and a second shared-memory
+//      transpose (7 STS + 2 LDS.128 + 7 adds) finishes the sum over the 8 pixel groups, leaving one
+//      output value per lane -> one red.global.add per value per (warp, instance).  ~60 issue slots per
+//      walk where a full shuffle reduction needs ~125.
 //   3. cp.async double-buffered staging of geometry + payload rows, float4 semantic rows, 8x4 pixel
-//      blocks per warp with the exact per-warp cull of goi_cull.cuh (ballot, walk set bits only),
-//      power_cut early reject, and the walk starts at the tile's deepest n_contrib.
+//      blocks per warp selected by the cull masks the FORWARD stored per list entry (no re-test here),
+//      and the walk starts at the tile's deepest n_contrib.
+//   4. A rejected lane is a Gaussian of alpha 0 (inv = 1, weight 0, recurrence unchanged): no per-value
+//      selects; the Gaussian index rides in the staged geometry record; shared-memory addresses of the
+//      walk live in laundered registers.
 // Summation order therefore differs from the reference (whose float atomics are themselves
 // order-nondeterministic); the gradient tolerance is 1e-3 of the tensor's max.
 #include "goi_internal.cuh"
@@ -60,7 +64,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     // Each value group owns PPG payload values and 2 of the 6 geometry values (mean2D.xy, conic.xyw, opacity).
     constexpr int PPG = (NPROD + 3) / 4;               // payload values per group
     constexpr int VPG = PPG + 2;                       // values per group
-    constexpr int NBLK = (VPG + 7) / 8;                // 8-value butterfly blocks per lane
+    constexpr int NBLK = (VPG + 7) / 8;                // 8-value output blocks per lane
     constexpr int DROWS = 7;                           // per hit: weight row + 6 geometry rows
     extern __shared__ float4 smem[];
     float4* s_g0 = smem;                               // [2][BATCH]
@@ -185,7 +189,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         cp_async_commit();
     };
 
-    // After the butterfly, block k of lane (pg, vg) holds group value u = 8k + pg:
+    // After the second-stage transpose, block k of lane (pg, vg) holds group value u = 8k + pg:
     //   u < PPG : payload value pv = vg*PPG + u  (pv < 3 colour | 3 depth | 4.. semantic pv-4)
     //   else    : geometry value gv = 2*vg + (u - PPG)  (0,1 mean2D.xy | 2,3,4 conic.x,.y,.w | 5 opacity)
     float* out_ptr[NBLK];
@@ -314,7 +318,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
                 sts32(ad + 6 * RSTRIDE * 4, Gh * dL_dopa);
                 __syncwarp();
 
-                // ---- reduction over the warp's 32 pixels: 4-pixel partial sums, then 8-lane butterfly ----
+                // ---- reduction over the warp's 32 pixels: 4-pixel partial sums, then the 8 pixel groups ----
                 const uint32_t ar = ad + dl;                                // this lane's 4 pixels in row 0
                 const float4 w4 = lds128(ar);
                 const float4 e0 = lds128(ar + go);

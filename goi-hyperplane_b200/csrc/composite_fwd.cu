@@ -12,13 +12,17 @@
 //
 // B200 design (what differs from the reference kernel):
 //   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block;
-//   * instances are staged 128 at a time into shared memory with cp.async (LDGSTS), double
-//     buffered, INCLUDING the payload row (rgb, depth, S semantic floats, float4-vectorised):
+//   * instances are staged 128 at a time into shared memory with cp.async (LDGSTS) in a ring of
+//     three stages, INCLUDING the payload row (rgb, depth, S semantic floats, float4-vectorised):
 //     the reference re-reads S+4 scalars from global memory per contributing pair (:360-364);
-//   * per-warp culling: the 32 lanes test 32 staged instances in parallel against the warp's 8x4
-//     pixel rectangle with the exact concave-quadratic bound of goi_cull.cuh, ballot, and the warp
-//     then walks only the set bits (in list order).  A rejected (warp, instance) costs ~1.5
-//     instructions instead of a full per-pixel evaluation;
+//   * culling one batch ahead of the walk: the CTA tests every staged instance against the eight 8x4
+//     warp blocks of the tile with the exact concave-quadratic bound of goi_cull.cuh (reciprocals paid
+//     once per instance), publishes an 8-bit mask per instance (shared memory for the walk, global
+//     memory for the backward); a warp ballots its bit over 32 instances and walks only the set bits
+//     (in list order).  A rejected (warp, instance) costs a fraction of an instruction instead of a
+//     full per-pixel evaluation;
+//   * the channel accumulation is packed FFMA2; with MASK the epilogue runs the hyperplane mask on the
+//     pixel accumulators (tensor-core projection + arg-max, goi_mask_mma.cuh);
 //   * power_cut (precomputed -ln(255 o) - margin) rejects provably non-contributing pixels
 //     before the expf;
 //   * S is a run-time value: kernels are instantiated per float4-group count (0..16 groups).
