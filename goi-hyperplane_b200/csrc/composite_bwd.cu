@@ -152,12 +152,12 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 #pragma unroll
     for (int k = 0; k < 2 * NS4; ++k) gs2[k] = make_float2(g_sem[2 * k], g_sem[2 * k + 1]);
 
-    {   // the walk only needs list entries [0, max n_contrib over the tile)
-        uint32_t m = last_contributor;
+    // the walk only needs list entries [0, max n_contrib over the tile); this warp only those below its own maximum
+    uint32_t warp_max_contrib = last_contributor;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
-        if (lane == 0 && m > 0) atomicMax(&s_max_contrib, m);
-    }
+    for (int off = 16; off >= 1; off >>= 1)
+        warp_max_contrib = max(warp_max_contrib, __shfl_xor_sync(0xffffffffu, warp_max_contrib, off));
+    if (lane == 0 && warp_max_contrib > 0) atomicMax(&s_max_contrib, warp_max_contrib);
     __syncthreads();
     const int n = (int)s_max_contrib;                  // entries [0,n) of this tile's list, walked backwards
     const int nb = (n + BATCH - 1) / BATCH;
@@ -255,7 +255,10 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
         const uint32_t apay = a_pay + buf * BATCH * ROW * 16;
         const int first_idx = n - 1 - b * BATCH;        // list index of j = 0
         for (int c0 = 0; c0 < cnt; c0 += 32) {
-            unsigned m = __ballot_sync(0xffffffffu, (c0 + lane < cnt) && ((s_cull[buf][c0 + lane] >> warp) & 1u));
+            // (entries at or behind every pixel's last contributor cannot blend here: pixels of this block that
+            //  saturated early make that a long stretch of the list in dense scenes)
+            unsigned m = __ballot_sync(0xffffffffu, (c0 + lane < cnt) && ((s_cull[buf][c0 + lane] >> warp) & 1u) &&
+                                                    (uint32_t)(first_idx - (c0 + lane)) < warp_max_contrib);
             GOI_STAT_ADD(0, (c0 + lane < cnt) ? 1u : 0u);
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
