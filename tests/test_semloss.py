@@ -65,6 +65,25 @@ def test_semloss_library_exports_every_declared_symbol():
     assert C.sizeof(sl.goi_semloss_args) == 152          # static_assert-ed in csrc/semloss.cu
 
 
+def test_semloss_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
+    """include/goi_semloss.h must compile as C99 (the boundary is a C ABI) and every field offset of the struct must
+    equal the ctypes mirror's."""
+    import subprocess
+    from goi_b200 import semantic_loss as sl
+    header = os.path.join(ROOT, "include", "goi_semloss.h")
+    fields = [f[0] for f in sl.goi_semloss_args._fields_ if not f[0].startswith("_pad")]
+    body = 'printf("size %zu\\n", sizeof(goi_semloss_args));\n'
+    body += "".join(f'printf("{f} %zu\\n", offsetof(goi_semloss_args, {f}));\n' for f in fields)
+    prog = tmp_path / "sl.c"
+    prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{header}"\nint main(){{\n{body}return 0;}}\n')
+    exe = tmp_path / "sl"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(prog), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert C.sizeof(sl.goi_semloss_args) == int(out["size"])
+    for f in fields:
+        assert getattr(sl.goi_semloss_args, f).offset == int(out[f]), f
+
+
 def test_product_never_imports_the_oracle():
     src = open(os.path.join(ROOT, "goi-hyperplane_b200", "goi_b200", "semantic_loss.py")).read()
     assert "oracle" not in src.replace("no CPU/eager fallback", "")
