@@ -125,6 +125,7 @@ ImageState carve_image(char* base, int W, int H)
     const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     obtain(c, s.ranges, tiles > 0 ? tiles : 1);
     obtain(c, s.n_contrib, (size_t)W * H > 0 ? (size_t)W * H : 1);
+    obtain(c, s.tile_order, tiles > 0 ? tiles : 1);
     s.total_bytes = (size_t)(c - base) + 256;
     return s;
 }

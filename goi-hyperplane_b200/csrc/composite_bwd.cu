@@ -47,8 +47,8 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp: x =
 
 template <int NS4, int BATCH>
 __global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 3 : NS4 <= 8 ? 2 : 1))
-k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                const uint32_t* __restrict__ cull, int W, int H, int gx,
+k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                const uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cull, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg, const float* __restrict__ out_alpha,
                 const uint32_t* __restrict__ n_contrib,
@@ -80,7 +80,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pg = lane & 7, vg = lane >> 3;
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];      // longest lists first (k_tile_order)
     const int tx = tile % gx, ty = tile / gx;
     const int wx0 = tx * TILE + (warp & 1) * 8, wy0 = ty * TILE + (warp >> 1) * 4;
     const int px = wx0 + (lane & 7);
@@ -378,7 +378,7 @@ static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const
     if (e != cudaSuccess) return e;
     const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
     kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(
-        is.ranges, point_list, cull, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S, sem_vec, v.background,
+        is.ranges, is.tile_order, point_list, cull, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S, sem_vec, v.background,
         in.out_alpha, is.n_contrib, in.dL_dcolor, in.dL_dsemantic, in.dL_ddepth, in.dL_dalpha,
         out.dL_dmean2D, out.dL_dconic, out.dL_dopacity, out.dL_dcolor, out.dL_dsemantic, out.dL_ddepth);
     count_launches(1);

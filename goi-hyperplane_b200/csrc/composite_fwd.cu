@@ -49,7 +49,8 @@ struct MaskEpilogue {
 
 template <int NS4, int BATCH, bool TRACE, bool MASK>
 __global__ void __launch_bounds__(COMPOSITE_THREADS, (NS4 <= 4 ? 4 : NS4 <= 8 ? 3 : 1))   // 64 registers: the mask epilogue may spill, the walk must not
-k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                const uint32_t* __restrict__ point_list, int W, int H, int gx,
                 const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                 int S, int sem_vec, const float* __restrict__ bg,
                 float* __restrict__ out_color, float* __restrict__ out_sem, float* __restrict__ out_depth,
@@ -68,7 +69,7 @@ k_composite_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ p
     __shared__ uint32_t s_cull[2][BATCH];              // per staged instance: 8-bit warp-block mask
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];      // longest lists first (k_tile_order)
     const int tx = tile % gx, ty = tile / gx;
     const int wx0 = tx * TILE + (warp & 1) * 8, wy0 = ty * TILE + (warp >> 1) * 4;   // warp's 8x4 block
     const int px = wx0 + (lane & 7);
@@ -279,7 +280,7 @@ static cudaError_t launch_fwd_t(const goi_view& v, const goi_gaussians& g, const
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
-    kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(is.ranges, point_list, v.width, v.height, gx, gs.geo, gs.rgbd,
+    kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(is.ranges, is.tile_order, point_list, v.width, v.height, gx, gs.geo, gs.rgbd,
                                                    g.semantics, g.S, sem_vec, v.background, out_color, out_sem,
                                                    out_depth, out_alpha, is.n_contrib, cull_out, img_sem, gau_sem,
                                                    num_gsem, count_per_channel, me);

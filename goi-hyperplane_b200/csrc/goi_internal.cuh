@@ -46,6 +46,7 @@ struct GeomState {
 struct ImageState {
     uint2*    ranges;            // [tiles]  [start,end) into point_list
     uint32_t* n_contrib;         // [H*W]    1-based index of the last blended list entry
+    uint32_t* tile_order;        // [tiles]  block b of the composites works on tile tile_order[b]: longest lists first
     size_t    total_bytes;
 };
 struct BinningState {
