@@ -108,6 +108,30 @@ def test_large_splats_match_reference_cuda(n_big, factor):
     assert _C.last_num_rendered == r1
 
 
+def test_dense_skewed_scene_matches_reference_cuda():
+    """Most splats squeezed into the bottom rows and made opaque: very uneven tile lists (exercises the
+    longest-list-first block order), pixels that saturate early (forward termination, the backward's per-warp
+    bound on the walk), against the reference kernels."""
+    S, P, W, H, seed = 16, 120_000, 480, 320, 9
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    with torch.no_grad():
+        n = int(0.8 * P)
+        z = g._xyz[:n, 2]
+        ymax = z * (H / W) * math.tan(math.radians(30.0))
+        g._xyz[:n, 1] = ymax * (1.0 - 0.1 * torch.rand(n, generator=torch.Generator().manual_seed(2)))
+        g._opacity[:n] = 0.6 + 0.39 * g._opacity[:n]
+    bg = torch.tensor([0.0, 0.3, 0.1])
+    w = make_loss_weights(S, W, H, seed)
+    ref = run_reference_cuda(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert torch.equal(cu["radii"].cpu(), ref["radii"].cpu())
+    assert float((to_np(ref["alpha"]) > 0.999).mean()) > 0.05          # a good part of the image really saturates
+    assert_images_close(cu, ref, max_bad_frac=0.0, what="dense skewed scene vs reference cuda")
+    assert_grads_close(cu["grads"], ref["grads"], what="dense skewed scene vs reference cuda")
+
+
 @pytest.mark.parametrize("P,W,H,S,seed", [(10_000, 256, 256, 10, 0), (8_000, 250, 197, 16, 3)])
 def test_oracle_pinned_by_reference_cuda(P, W, H, S, seed):
     """The CPU oracle itself is checked against the real reference kernels (parity pin)."""
