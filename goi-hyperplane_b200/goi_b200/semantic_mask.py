@@ -67,23 +67,3 @@ class SemanticHyperplane:
     def select_gaussians(self, gaussian_semantics):
         """[P,S] -> bool [P] (gui/main.py:400-405 compute_relative_gs_index)."""
         return self.compute_similarity(gaussian_semantics) > 0
-
-
-def torch_reference_similarity(x, mlp_weight, mlp_bias, lut, w, log_scale=0.0, thresh=0.86, osh_bias=None):
-    """The reference's own torch op chain, kept verbatim in structure for tests (gui/main.py:365-384)."""
-    dec = torch.nn.functional.linear(x, mlp_weight, mlp_bias)
-    idx = torch.softmax(dec * 10, dim=-1).argmax(dim=-1)
-    f = lut[idx]
-    f = f / f.norm(dim=-1, keepdim=True)
-    if osh_bias is not None:
-        sim = torch.nn.functional.linear(f / 0.3438, w.reshape(1, -1), torch.tensor([osh_bias], device=x.device))
-        sim = sim.squeeze().sigmoid()
-        thresh = 0.5
-    else:
-        logit = torch.matmul(f, w.reshape(1, -1).transpose(-1, -2)) / math.exp(log_scale)
-        logit = torch.clamp(torch.clamp(logit, max=50000), min=-50000) + 2
-        sim = logit.sigmoid().squeeze(-1)
-    bg = sim < thresh
-    sim = sim.clone()
-    sim[bg] = 0
-    return sim, bg, idx

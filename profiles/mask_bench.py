@@ -11,11 +11,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "goi-hyperplane_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 from bench import CONFIGS, make_views  # noqa: E402
 from gaussian_renderer import render, render_mask  # noqa: E402
 from goi_b200.scenes import PipeFlags, make_mask_model, make_scene  # noqa: E402
-from goi_b200.semantic_mask import SemanticHyperplane, torch_reference_similarity  # noqa: E402
+from goi_b200.semantic_mask import SemanticHyperplane  # noqa: E402
+from common import torch_reference_similarity  # noqa: E402  (tests/common.py)
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 P, W, H, S, seed = CONFIGS[cfg]

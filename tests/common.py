@@ -180,3 +180,51 @@ def assert_grads_close(a, b, rtol=GRAD_RTOL, what="", keys=GRAD_KEYS):
     for k, r in rep.items():
         assert r["rel"] <= rtol, f"{what} {k}: max|diff|/max|ref| = {r['rel']:.3e} > {rtol}"
     return rep
+
+
+# ---- mask goldens (tests/golden/mask_*.npz, cut from the reference's own gui/main.py by make_mask_golden.py) ----
+def mask_golden_args(z):
+    """Keyword arguments for oracle.mask / SemanticHyperplane from one golden file: APE uses the text hyperplane
+    + log_scale + threshold, OSH the LinearSVM weight/bias with the reference's fixed 0.5 threshold."""
+    osh = int(z["meta"][4]) == 1
+    if osh:
+        return dict(w=z["svm_weight"].reshape(-1), mode=1, hyperplane_b=float(z["svm_bias"][0]), log_scale=0.0,
+                    thresh=0.5)
+    return dict(w=z["text"].reshape(-1), mode=0, hyperplane_b=0.0, log_scale=float(z["log_scale"]),
+                thresh=float(z["thresh"]))
+
+
+def assert_mask_matches_golden(got_sim, got_bg, got_idx, z, what, gap_eps=1e-5):
+    """Exact codebook row / mask except where the reference's own top-2 logit gap is below gap_eps (arg-max
+    near-ties: summation-order effects); sim within the north star's 1e-4.  Returns the exemption count."""
+    near = z["top2_gap"] <= gap_eps
+    clear = ~near
+    assert near.mean() < 1e-2, f"{what}: {near.sum()} near-ties of {near.size}"
+    assert np.array_equal(np.asarray(got_idx)[clear], z["idx"][clear]), f"{what}: codebook rows differ"
+    d = np.abs(np.asarray(got_sim, np.float64)[clear] - z["sim"].astype(np.float64)[clear])
+    # a sim within 1e-6 of the threshold may land on either side (the output is then 0 or ~thresh): exempt + count
+    flips = np.asarray(got_bg)[clear] != z["bg_mask"][clear]
+    assert flips.sum() <= 2, f"{what}: {flips.sum()} threshold flips"
+    assert d[~flips].max() <= IMG_TOL, f"{what}: sim L-inf {d[~flips].max():.3e}"
+    return dict(near_ties=int(near.sum()), threshold_flips=int(flips.sum()), linf=float(d[~flips].max()))
+
+
+def torch_reference_similarity(x, mlp_weight, mlp_bias, lut, w, log_scale=0.0, thresh=0.86, osh_bias=None):
+    """The reference's torch op chain restated for the GPU tests (gui/main.py:365-384); the pinned comparison is
+    against tests/golden/mask_*.npz, which the reference's own source produced."""
+    dec = torch.nn.functional.linear(x, mlp_weight, mlp_bias)
+    idx = torch.softmax(dec * 10, dim=-1).argmax(dim=-1)
+    f = lut[idx]
+    f = f / f.norm(dim=-1, keepdim=True)
+    if osh_bias is not None:
+        sim = torch.nn.functional.linear(f / 0.3438, w.reshape(1, -1), torch.tensor([osh_bias], device=x.device))
+        sim = sim.squeeze().sigmoid()
+        thresh = 0.5
+    else:
+        logit = torch.matmul(f, w.reshape(1, -1).transpose(-1, -2)) / math.exp(log_scale)
+        logit = torch.clamp(torch.clamp(logit, max=50000), min=-50000) + 2
+        sim = logit.sigmoid().squeeze(-1)
+    bg = sim < thresh
+    sim = sim.clone()
+    sim[bg] = 0
+    return sim, bg, idx

@@ -10,7 +10,8 @@ import torch
 
 import common
 from goi_b200.scenes import make_loss_weights, make_mask_model, make_scene
-from goi_b200.semantic_mask import SemanticHyperplane, torch_reference_similarity
+from common import torch_reference_similarity
+from goi_b200.semantic_mask import SemanticHyperplane
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -32,6 +33,34 @@ def test_cuda_matches_reference_cuda_golden(path):
     keys = [k for k in cu["grads"] if cu["grads"][k] is not None and k in z.files]
     assert len(keys) >= 5
     common.assert_grads_close(cu["grads"], {k: z[k] for k in keys}, what="cuda vs reference golden", keys=keys)
+
+
+MASK_FILES = sorted(glob.glob(os.path.join(GOLDEN, "mask_*.npz")))
+
+
+@pytest.mark.parametrize("channels_first", [False, True])
+@pytest.mark.parametrize("path", MASK_FILES, ids=[os.path.basename(p) for p in MASK_FILES])
+def test_mask_kernel_matches_reference_golden(path, channels_first):
+    """goi_mask (k_mask_table + k_mask_apply) against vectors the reference's own gui/main.py:363-385 +
+    vision_language_align.py:109-122 + networks.py LinearSVM + semantic_model.py produced
+    (tests/golden/make_mask_golden.py).  [N,S] row-major = the per-Gaussian 3D selection form, channels_first = the
+    planar render output."""
+    z = np.load(path)
+    assert len(MASK_FILES) >= 4
+    kw = common.mask_golden_args(z)
+    t = lambda a: torch.tensor(np.ascontiguousarray(a)).cuda()
+    hp = SemanticHyperplane(t(z["mlp_weight"]), t(z["mlp_bias"]), t(z["lut"]), t(kw["w"]), log_scale=kw["log_scale"],
+                            thresh=kw["thresh"])
+    if kw["mode"] == 1:
+        hp.enable_osh(bias=kw["hyperplane_b"])
+    x = t(z["x"])
+    N = x.shape[0]
+    xin = x.t().contiguous() if channels_first else x
+    bg = torch.zeros(N, dtype=torch.bool, device="cuda")
+    sim, idx = hp.compute_similarity(xin, out_bg_mask=bg, channels_first=channels_first, want_idx=True)
+    rep = common.assert_mask_matches_golden(sim.cpu().numpy(), bg.cpu().numpy(), idx.cpu().numpy(), z,
+                                            "goi_mask vs reference golden")
+    print("\n", os.path.basename(path), rep)
 
 
 @pytest.mark.parametrize("S,N,mode,channels_first", [(16, 200_000, "ape", False), (10, 50_000, "ape", True),

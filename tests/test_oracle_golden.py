@@ -165,3 +165,25 @@ def test_oracle_trace_and_mark_visible():
     assert np.allclose(a["gau_sem"], b["gau_sem"])
     fwd = oracle.forward(**common.gaussian_arrays(g), **ca)
     assert np.abs(fwd.color - a["color"]).max() < 1e-6           # same composite for the colour image
+
+
+# ---------------------------------------------------------------------------------------------
+# mask path: the oracle against goldens cut from the reference's own gui/main.py / vision_language_align.py /
+# networks.py / semantic_model.py (tests/golden/make_mask_golden.py)
+# ---------------------------------------------------------------------------------------------
+MASK_FILES = sorted(glob.glob(os.path.join(GOLDEN, "mask_*.npz")))
+
+
+def test_mask_golden_files_present():
+    assert len(MASK_FILES) >= 4
+
+
+@pytest.mark.parametrize("path", MASK_FILES, ids=[os.path.basename(p) for p in MASK_FILES])
+def test_oracle_mask_matches_reference_golden(path):
+    z = np.load(path)
+    kw = common.mask_golden_args(z)
+    o = oracle.mask(z["x"], z["mlp_weight"], z["mlp_bias"], z["lut"], kw.pop("w"), **kw)
+    rep = common.assert_mask_matches_golden(o["sim"], o["bg_mask"], o["idx"], z, "oracle mask vs reference golden")
+    # the oracle's own near-tie measure must agree with the reference's logits
+    assert np.abs(o["top2_gap"] - z["top2_gap"]).max() <= 1e-5
+    print(rep)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from goi_b200.scenes import make_mask_model, make_scene
-from goi_b200.semantic_mask import torch_reference_similarity
+from common import torch_reference_similarity
 from oracle import oracle
 
 
