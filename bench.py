@@ -112,6 +112,18 @@ def make_views(W, H, device):
     return cams
 
 
+def build_workload(config, dev):
+    """(gaussians, cameras, background) of a config: SURVEY.md section 8d.  c4 is the object-centric orbit scene (64
+    cameras on a circle looking at the origin), the others the frustum-filling scene with 8 jittered poses."""
+    from goi_b200.scenes import make_orbit_scene, make_scene
+    P, W, H, S, seed = CONFIGS[config]
+    if config == "c4":
+        g, cams, bg = make_orbit_scene(P, W, H, S, 64, seed)
+        return g.to(dev), [c.to(dev) for c in cams], bg.to(dev)
+    g, _, bg = make_scene(P, W, H, S, seed)
+    return g.to(dev), make_views(W, H, dev), bg.to(dev)
+
+
 def ncu_reference(config):
     """DRAM bytes and executed warp instructions of the two composite kernels from the committed `ncu --set full`
     capture (profiles/traffic.json), for roofline.traffic and the issue-slot companion bound; None if the capture
@@ -129,6 +141,26 @@ def ncu_reference(config):
         return None
 
 
+def metric_name(config):
+    """BASELINE.json's metric string for the config it is quoted on (c2); the same sentence with the config's own
+    sizes for the others, so a line can never be mistaken for the headline."""
+    P, W, H, S, _ = CONFIGS[config]
+    pm = f"{P // 1_000_000}M" if P % 1_000_000 == 0 else f"{P // 1000}k"
+    return f"views/sec fwd+bwd @{pm} Gaussians,{W}x{H},{S}ch; HBM GB/s vs roofline"
+
+
+def config_dict(args, world, vps, num_rendered_mean):
+    """`config` of the JSON line -- the SAME key set for both arms (only num_rendered_mean differs in value: this
+    build culls provably empty tile instances, the reference walks its full rectangles)."""
+    P, W, H, S, _ = CONFIGS[args.config]
+    return {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
+                        f"fwd+bwd of all four outputs, {64 if args.config == 'c4' else N_VIEWS} camera poses",
+            "views_per_step": world * vps, "views_per_gpu_per_step": vps,
+            "parallelism": f"view-dp{world}, one all-reduce of the per-Gaussian gradients per step",
+            "l2_policy": "inputs larger than L2 (300 MB parameters + 98 MB sort buffers per view)",
+            "num_rendered_mean": round(num_rendered_mean)}
+
+
 def b_comp(R, W, H, S):
     """algorithmic bytes of forward + backward composite for one view."""
     T = ((W + 15) // 16) * ((H + 15) // 16)
@@ -139,7 +171,7 @@ def run_ours(args):
     import torch.distributed as dist
     from diff_gaussian_rasterization import _C
     from gaussian_renderer import render
-    from goi_b200.scenes import PipeFlags, make_loss_weights, make_scene
+    from goi_b200.scenes import PipeFlags, make_loss_weights
     from goi_b200 import view_parallel as vp
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,10 +184,9 @@ def run_ours(args):
     _C.lib()        # hard error if the CUDA library is missing: no fallback path
 
     P, W, H, S, seed = CONFIGS[args.config]
-    g, _, bg = make_scene(P, W, H, S, seed)
-    g = g.to(dev).requires_grad_(True)
-    bg = bg.to(dev)
-    cams = make_views(W, H, dev)
+    g, cams, bg = build_workload(args.config, dev)
+    g = g.requires_grad_(True)
+    n_cams = len(cams)
     pipe = PipeFlags()
     w_dev = make_loss_weights(S, W, H, seed, device=dev)
     # the backward writes the parameter gradients straight into slices of ONE flat buffer (all-reduce operand)
@@ -174,7 +205,7 @@ def run_ours(args):
         64 views over 8 GPUs the same way: 8 views per rank per all-reduce)."""
         for v in range(vps):
             view = i * vps + v                       # this rank's running view counter
-            cam = cams[(view * world + rank) % N_VIEWS]
+            cam = cams[(view * world + rank) % n_cams]
             wv = weights(view) if callable(weights) else weights
             arena.clear_grads()
             out = render(cam, g, pipe, bg)
@@ -216,7 +247,7 @@ def run_ours(args):
 
     def resident_step(i):
         step(i, w_dev)
-        rs.append(_C.last_num_rendered)       # (of the step's last view; the poses differ by a few degrees)
+        rs.append(_C.num_rendered())       # (of the step's last view; the poses differ by a few degrees)
 
     ms_total = timed(resident_step, args.steps)
     # per-stage CUDA-event times of the timed region's views (ring of the last 64), read after the region
@@ -302,16 +333,11 @@ def run_ours(args):
     bytes_comp = b_comp(R, W, H, S)
     achieved = bytes_comp / t_comp / 1e9 if t_comp > 0 else 0.0
     line = {
-        "metric": "views/sec fwd+bwd @1M Gaussians,1600x1000,16ch; HBM GB/s vs roofline",
+        "metric": metric_name(args.config),
         "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
-                               f"fwd+bwd of all four outputs, {N_VIEWS} camera poses",
-                   "views_per_step": world * vps, "views_per_gpu_per_step": vps,
-                   "parallelism": f"view-dp{world}, one all-reduce of the flat f32 gradient buffer per step",
-                   "l2_policy": "inputs larger than L2 (300 MB parameters + 98 MB sort buffers per view)",
-                   "num_rendered_mean": round(R)},
+        "config": config_dict(args, world, vps, R),
         "clocks": clocks,
         "ms_per_view": round(ms_total / args.steps / vps, 4),
         "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes * vps,
@@ -353,63 +379,95 @@ def cpu_baseline(args):
 
 
 def run_reference(args):
-    """The reference's own CUDA kernels + glue (oracle/_ref/libref_S*.so) on the same workload."""
+    """The reference's own CUDA kernels + glue (oracle/_ref/libref_S*.so) on the same workload, on EVERY rank: N
+    independent single-GPU replicas of the reference (it has no multi-GPU path, utils/general_utils.py:144), each
+    rendering `views_per_step` views per step with the per-view gradients summed the way its autograd would
+    (AccumulateGrad: one add per tensor per view), and a torch NCCL all-reduce of those gradient tensors per step
+    (SURVEY.md section 8d)."""
+    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from oracle import refshim
-    from goi_b200.scenes import make_loss_weights, make_scene
+    from goi_b200.scenes import make_loss_weights
     P, W, H, S, seed = CONFIGS[args.config]
     if not refshim.available(S):
-        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libref_S{S}.so not built"}))
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libref_S{S}.so not built"}))
         return
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
-    g, _, bg = make_scene(P, W, H, S, seed)
-    g = g.to(dev)
-    bg = bg.to(dev)
-    cams = make_views(W, H, dev)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g, cams, bg = build_workload(args.config, dev)
+    n_cams = len(cams)
     w = {k: v.contiguous() for k, v in make_loss_weights(S, W, H, seed, device=dev).items()}
     rr = refshim.RefRasterizer(S)
     tensors = dict(means3D=g.get_xyz.contiguous(), opacities=g.get_opacity.contiguous(),
                    shs=g.get_features.contiguous(), semantics=g.get_semantics.contiguous(),
                    scales=g.get_scaling.contiguous(), rotations=g.get_rotation.contiguous())
+    vps = args.views_per_step
+    param_grads = ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dsh", "dL_dsemantics")
+    rs = []
 
     def step(i):
-        cam = cams[i % N_VIEWS]
-        rr.forward(W=W, H=H, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
-                   campos=cam.camera_center, tanfovx=math.tan(cam.FoVx / 2), tanfovy=math.tan(cam.FoVy / 2), bg=bg,
-                   **tensors)
-        rr.backward(w["render"], w["semantics"], w["depth"], w["alpha"])
+        total = None
+        for v in range(vps):
+            view = i * vps + v
+            cam = cams[(view * world + rank) % n_cams]
+            rr.forward(W=W, H=H, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+                       campos=cam.camera_center, tanfovx=math.tan(cam.FoVx / 2), tanfovy=math.tan(cam.FoVy / 2), bg=bg,
+                       **tensors)
+            gr = rr.backward(w["render"], w["semantics"], w["depth"], w["alpha"])
+            if total is None:
+                total = {k: gr[k] for k in param_grads}
+            else:
+                for k in param_grads:
+                    total[k] += gr[k]                  # autograd's AccumulateGrad
+        if world > 1:
+            for k in param_grads:
+                dist.all_reduce(total[k], op=dist.ReduceOp.SUM)
+        rs.append(rr.num_rendered)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for i in range(args.warmup):
         step(i)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+    del rs[:]
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    value = args.steps / (ms / 1e3)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    if rank != 0:
+        return
+    value = world * vps * args.steps / (ms / 1e3)
     line = {
         "impl": "reference",
-        "metric": "views/sec fwd+bwd @1M Gaussians,1600x1000,16ch; HBM GB/s vs roofline",
-        "value": round(value, 3), "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.config),
+        "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
-                               f"fwd+bwd of all four outputs, {N_VIEWS} camera poses",
-                   "num_rendered": rr.num_rendered, "requested_gpus": world},
+        "config": config_dict(args, world, vps, sum(rs) / max(len(rs), 1)),
         "clocks": clocks,
-        "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": 1, "kind": "reference",
+        "ms_per_view": round(ms / args.steps / vps, 4),
+        "reference_class": "gpu",
+        "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": world, "kind": "reference",
                          "sample": "the reference's own CUDA rasterizer (cuda_rasterizer/*.cu compiled unmodified "
-                                   "for sm_100a) driven by a single host thread incl. its blocking num_rendered "
+                                   "for sm_100a) driven by one host thread per GPU incl. its blocking num_rendered "
                                    "read-back and zero fills; the reference has no CPU rasterizer"},
         "e2e": {"value": round(value, 3), "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -134,7 +134,6 @@ BinningState carve_binning(char* base, int64_t R)
     BinningState b{};
     char* c = base;
     const size_t Rn = (size_t)(R > 0 ? R : 1);
-    obtain(c, b.header, 64);
     obtain(c, b.keys[0], Rn);
     obtain(c, b.keys[1], Rn);
     obtain(c, b.vals[0], Rn);

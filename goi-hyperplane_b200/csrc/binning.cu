@@ -24,23 +24,39 @@
 
 namespace goi {
 
-size_t scan_temp_bytes_for(int P)
-{
-    // Upper bound on cub::DeviceScan temp storage (tile descriptors, a few bytes per 1-2K items);
-    // checked against CUB's own answer at run time in run_scan().
-    return (size_t)P / 64 + (64u << 10);
-}
-size_t sort_temp_bytes_for(int64_t R)
-{
-    // Upper bound for cub::DeviceRadixSort (DoubleBuffer form: histograms + decoupled look-back
-    // descriptors only); checked at run time.
-    return (size_t)(R > 0 ? R : 0) / 4 + (1u << 20);
-}
-
 struct GatherTiles {
     const uint32_t* tiles;
     __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& idx) const { return tiles[idx]; }
 };
+
+// Temp-storage sizes come from CUB itself (the size-query form: null temp pointer, no launch, no stream work), asked
+// when a blob is carved.  The queries are pure host arithmetic on the item count; the last answer is cached per thread
+// because every entry point carves the same blobs again.
+size_t scan_temp_bytes_for(int P)
+{
+    static thread_local int last_P = -1;
+    static thread_local size_t last = 0;
+    if (P == last_P) return last;
+    size_t need = 0;
+    cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*> it(nullptr, GatherTiles{nullptr});
+    if (cub::DeviceScan::InclusiveSum(nullptr, need, it, (uint32_t*)nullptr, P > 0 ? P : 1) != cudaSuccess) need = 0;
+    last_P = P;
+    last = need + 256;
+    return last;
+}
+size_t sort_temp_bytes_for(int64_t R)
+{
+    static thread_local int64_t last_R = -1;
+    static thread_local size_t last = 0;
+    if (R == last_R) return last;
+    // all 32 key bits: an upper bound for any [0, end_bit) the run-time sort uses (fewer passes, fewer histograms)
+    cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+    size_t need = 0;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, R > 0 ? R : 1, 0, 32) != cudaSuccess) need = 0;
+    last_R = R;
+    last = need + 256;
+    return last;
+}
 
 // Stage 1 + prefix sum: depth-sort the Gaussians, then scan their instance counts in depth order.
 cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st)
@@ -138,22 +154,25 @@ __global__ void __launch_bounds__(256) k_emit_keys(int P, const uint32_t* __rest
     }
 }
 
+// [start, end) of every tile's run in the sorted key array (replaces identifyTileRanges, rasterizer_impl.cu:116-138;
+// `ranges` is zeroed beforehand, so tiles without instances keep the empty range).  A CTA loads 256 consecutive keys
+// once (coalesced) plus one halo key; position i is a run boundary iff key[i-1] != key[i], and a boundary closes the
+// left tile's run and opens the right one's.
 __global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint32_t* __restrict__ keys,
                                                      uint2* __restrict__ ranges)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t currtile = keys[idx];
-    if (idx == 0)
-        ranges[currtile].x = 0;
-    else {
-        const uint32_t prevtile = keys[idx - 1];
-        if (currtile != prevtile) {
-            ranges[prevtile].y = (uint32_t)idx;
-            ranges[currtile].x = (uint32_t)idx;
-        }
+    __shared__ uint32_t s_key[257];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < L) s_key[threadIdx.x + 1] = keys[i];
+    if (threadIdx.x == 0) s_key[0] = (i > 0 && i <= L) ? keys[i - 1] : 0xffffffffu;      // no tile has this id
+    __syncthreads();
+    if (i >= L) return;
+    const uint32_t left = s_key[threadIdx.x], here = s_key[threadIdx.x + 1];
+    if (left != here) {
+        ranges[here].x = (uint32_t)i;
+        if (i > 0) ranges[left].y = (uint32_t)i;
     }
-    if (idx == L - 1) ranges[currtile].y = (uint32_t)L;
+    if (i == L - 1) ranges[here].y = (uint32_t)L;
 }
 
 // Longest-list-first block order for the composites (one CTA, T tiles): the hardware hands out blocks in index order,
@@ -225,17 +244,11 @@ static cudaError_t launch_tile_order(int T, const uint2* ranges, uint32_t* order
     return cudaGetLastError();
 }
 
-// getHigherMsb, rasterizer_impl.cu:35-50: number of bits needed for the tile id.
-static uint32_t higher_msb(uint32_t n)
+// Radix-sort bit range of the tile id: ids are 0 .. tiles-1 (the reference sorts [0, 32 + getHigherMsb(tiles)),
+// rasterizer_impl.cu:304-312; here the depth half of the key was sorted separately).
+static int tile_id_bits(uint32_t tiles)
 {
-    uint32_t msb = sizeof(n) * 4;
-    uint32_t step = msb;
-    while (step > 1) {
-        step /= 2;
-        if (n >> msb) msb += step; else msb -= step;
-    }
-    if (n >> msb) msb++;
-    return msb;
+    return tiles > 1 ? 32 - __builtin_clz(tiles - 1) : 1;
 }
 
 cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const GeomState& gs,
@@ -260,7 +273,7 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
-    const int end_bit = (int)higher_msb((uint32_t)(gx * gy));
+    const int end_bit = tile_id_bits((uint32_t)(gx * gy));
     cub::DoubleBuffer<uint32_t> dk(bs.keys[0], bs.keys[1]);
     cub::DoubleBuffer<uint32_t> dv(bs.vals[0], bs.vals[1]);
     size_t need = 0;

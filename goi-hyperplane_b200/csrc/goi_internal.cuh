@@ -22,7 +22,7 @@ struct Meta {
 // Geometry scratch ("geomBuffer"): per-Gaussian records produced by preprocess and
 // consumed by binning, both composites and the per-Gaussian backward.
 //   geo[2i+0] = (mean2D.x, mean2D.y, conic.x, conic.y)
-//   geo[2i+1] = (conic.z, opacity, power_cut, 0)
+//   geo[2i+1] = (conic.z, opacity, power_cut, bits(i))   -- the Gaussian index rides along: both composites read it
 //   rgbd[i]   = (r, g, b, view-space depth)        -- the non-semantic payload of an instance
 //   rect[i]   = (minx | miny<<16, maxx | maxy<<16) -- tile rectangle of getRect()
 struct GeomState {
@@ -51,11 +51,10 @@ struct ImageState {
 };
 struct BinningState {
     uint32_t* keys[2];           // double buffer: tile id (instances are emitted in depth order)
-    uint32_t* vals[2];           // double buffer: Gaussian index; after the sort [0] = list, [1] = cull masks
-    uint32_t* selector;          // (device) unused; host keeps the selector in the header word below
+    uint32_t* vals[2];           // double buffer: Gaussian index; after the sort [0] = list (copied there if the
+                                 // sort ended in [1]), [1] = the forward's per-entry warp-block cull masks
     char*     sort_temp;
-    size_t    sort_temp_bytes;
-    uint32_t* header;            // [64] word 0 = which half of the double buffers holds the sorted list
+    size_t    sort_temp_bytes;   // CUB's own answer for this item count (sort_temp_bytes_for)
     size_t    total_bytes;
 };
 
@@ -73,7 +72,7 @@ inline int sem_groups(int S) {           // float4 groups the composite kernels 
     return 16;
 }
 
-// ---- measurement hooks (thread-local; see goi_timing_enable in goi_raster.h) -------------------
+// ---- measurement hooks (process-wide, mutex-guarded: autograd's backward runs on another thread; api.cu) -----
 enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES, ST_COMPOSITE_FWD, ST_ZERO, ST_COMPOSITE_BWD,
              ST_PREPROCESS_BWD, ST_COUNT };
 void stage_begin(Stage s, cudaStream_t st);

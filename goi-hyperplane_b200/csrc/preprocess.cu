@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool in_range = idx < P;
     const bool active = in_range && (radii[idx] > 0);
+    const bool rot_vec = (reinterpret_cast<uintptr_t>(dL_drot) & 15) == 0;
     float* tile = s_sh[warp];
     const int rowlen = 3 * M;
     const int base = blockIdx.x * blockDim.x + warp * 32;
@@ -775,11 +776,19 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
         }
         if (acc) {
             dsc.x += dL_dscale[3 * idx + 0]; dsc.y += dL_dscale[3 * idx + 1]; dsc.z += dL_dscale[3 * idx + 2];
-            const float4 o = *reinterpret_cast<const float4*>(dL_drot + 4 * idx);
-            dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+            // (the OUTPUT pointer may be a slice of a caller's flat buffer at any 4-byte offset: vector access only
+            //  when it is 16-byte aligned)
+            if (rot_vec) {
+                const float4 o = *reinterpret_cast<const float4*>(dL_drot + 4 * idx);
+                dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+            } else {
+                dq.x += dL_drot[4 * idx + 0]; dq.y += dL_drot[4 * idx + 1];
+                dq.z += dL_drot[4 * idx + 2]; dq.w += dL_drot[4 * idx + 3];
+            }
         }
         dL_dscale[3 * idx + 0] = dsc.x; dL_dscale[3 * idx + 1] = dsc.y; dL_dscale[3 * idx + 2] = dsc.z;
-        *reinterpret_cast<float4*>(dL_drot + 4 * idx) = dq;
+        if (rot_vec) *reinterpret_cast<float4*>(dL_drot + 4 * idx) = dq;
+        else { dL_drot[4 * idx + 0] = dq.x; dL_drot[4 * idx + 1] = dq.y; dL_drot[4 * idx + 2] = dq.z; dL_drot[4 * idx + 3] = dq.w; }
     }
 }
 

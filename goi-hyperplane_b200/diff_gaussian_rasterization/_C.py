@@ -115,32 +115,73 @@ SYMBOLS = {
     "goi_launch_count": (C.c_uint64, []),
 }
 GOI_NUM_STAGES = 9
-# Optional gradient arena: {name: preallocated tensor} for the parameter gradients "means3D", "sh",
-# "semantics", "opacities", "scales", "rotations", "colors_precomp", "cov3D_precomp".  When set, the backward
-# writes those gradients straight into the given tensors (e.g. slices of one flat all-reduce buffer, see
-# goi_b200/view_parallel.py) instead of fresh allocations -- no packing copy before the collective.
-# With accumulate=True the library ADDS each view's parameter gradients to what the arena already holds
-# (goi_bwd_out.accumulate): several views per rank summed in place, one all-reduce at the end.
-grad_arena = None
-grad_accumulate = False
+# Optional gradient arena, PER DEVICE: {name: preallocated tensor} for the parameter gradients "means3D", "sh",
+# "semantics", "opacities", "scales", "rotations", "colors_precomp", "cov3D_precomp".  When a device has one, the
+# backward of a rasterization on THAT device writes those gradients straight into the given tensors (e.g. slices of
+# one flat all-reduce buffer, see goi_b200/view_parallel.py) instead of fresh allocations -- no packing copy before
+# the collective.  With accumulate=True the library ADDS each view's parameter gradients to what the arena already
+# holds (goi_bwd_out.accumulate): several views per rank summed in place, one all-reduce at the end.
+# Keyed by device index rather than thread-local: autograd runs backward on its own worker thread (one per device),
+# so the thread that installs the arena is not the thread that consumes it.  All mutable binding state lives in
+# _DeviceState objects guarded by one lock; the C library below it is re-entrant per (device, stream).
+import threading
 
 
-def set_grad_arena(arena, accumulate=False):
-    global grad_arena, grad_accumulate
-    grad_arena = arena
-    grad_accumulate = bool(accumulate) and arena is not None
+class _DeviceState:
+    __slots__ = ("grad_arena", "grad_accumulate", "r_guess", "last_num_rendered")
+
+    def __init__(self):
+        self.grad_arena = None
+        self.grad_accumulate = False
+        self.r_guess = 0                 # running upper estimate of the instance count (sizes the binning blob)
+        self.last_num_rendered = 0       # R of the most recent forward on this device
 
 
-def _grad_out(name, shape, f32):
-    if grad_arena is not None and name in grad_arena:
-        t = grad_arena[name]
+_state_lock = threading.Lock()
+_states: dict = {}
+
+
+def _dev_index(device) -> int:
+    device = torch.device(device) if not isinstance(device, torch.device) else device
+    if device.type != "cuda":
+        return -1
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
+def device_state(device) -> _DeviceState:
+    i = _dev_index(device)
+    with _state_lock:
+        st = _states.get(i)
+        if st is None:
+            st = _states[i] = _DeviceState()
+        return st
+
+
+def set_grad_arena(arena, accumulate=False, device=None):
+    """Install (or with arena=None remove) the gradient arena of `device` (default: the arena tensors' device, else
+    the current CUDA device)."""
+    if device is None:
+        device = next(iter(arena.values())).device if arena else torch.device("cuda", torch.cuda.current_device())
+    st = device_state(device)
+    with _state_lock:
+        st.grad_arena = arena
+        st.grad_accumulate = bool(accumulate) and arena is not None
+
+
+def num_rendered(device=None) -> int:
+    """Instance count R of the most recent forward on `device` (bench.py's roofline arithmetic)."""
+    return device_state(device if device is not None else torch.device("cuda", torch.cuda.current_device())).last_num_rendered
+
+
+def _grad_out(st, name, shape, f32):
+    arena = st.grad_arena
+    if arena is not None and name in arena:
+        t = arena[name]
         if t.numel() != int(torch.Size(shape).numel()) or not t.is_contiguous():
             raise RuntimeError(f"grad arena entry {name!r} has {t.numel()} elements, expected shape {tuple(shape)}")
         return t.view(shape)
     return torch.empty(shape, **f32)
 
-_r_guess = 0               # running upper estimate of the instance count (sizes the binning blob)
-last_num_rendered = 0      # R of the most recent forward on this thread (bench.py's roofline arithmetic)
 
 _lib = None
 
@@ -258,8 +299,8 @@ def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotatio
         # The binning blob is sized BEFORE the instance count is known (a guess from recent views, with
         # headroom), so prepare + render run inside one C call and the device is refilled right after the
         # one host sync of the path; a wrong guess costs one re-allocation.
-        global _r_guess
-        bin_bytes = L.goi_binning_bytes(max(int(_r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
+        st = device_state(dev)
+        bin_bytes = L.goi_binning_bytes(max(int(st.r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
         binning = torch.empty((bin_bytes,), **u8)
         rc = L.goi_forward_auto(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
                                 binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, stream, C.byref(R))
@@ -269,9 +310,8 @@ def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotatio
             rc = L.goi_forward_render(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
                                       binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, R.value, stream)
         _check(rc, "goi_forward")
-        _r_guess = max(R.value, int(0.9 * _r_guess))
-    global last_num_rendered
-    last_num_rendered = int(R.value)
+        st.r_guess = max(R.value, int(0.9 * st.r_guess))
+        st.last_num_rendered = int(R.value)
     return int(R.value), out_color, out_sem, out_depth, out_alpha, radii, geom, binning, img
 
 
@@ -296,14 +336,17 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, 
                            _f32(dL_dout_depth, "dL_dout_depth"), _f32(dL_dout_alpha, "dL_dout_alpha"))
         alphas = _f32(alphas, "alphas")
         keep += [gc, gs_, gd, ga, alphas]
+        st = device_state(dev)
+        with _state_lock:
+            grad_arena, grad_accumulate = st.grad_arena, st.grad_accumulate
         # fully written (or zero-initialised) inside the library: torch.empty, not torch.zeros
-        dL_dmeans3D = _grad_out("means3D", (P, 3), f32)
+        dL_dmeans3D = _grad_out(st, "means3D", (P, 3), f32)
         dL_dmeans2D = torch.empty((P, 3), **f32)
-        dL_dcolors = _grad_out("colors_precomp", (P, 3), f32) if g.colors_precomp is not None else torch.empty((P, 3), **f32)
-        dL_dsemantics = _grad_out("semantics", (P, S), f32)
+        dL_dcolors = _grad_out(st, "colors_precomp", (P, 3), f32) if g.colors_precomp is not None else torch.empty((P, 3), **f32)
+        dL_dsemantics = _grad_out(st, "semantics", (P, S), f32)
         dL_ddepths = torch.empty((P, 1), **f32)
         dL_dconic = torch.empty((P, 2, 2), **f32)
-        dL_dopacity = _grad_out("opacities", (P, 1), f32)
+        dL_dopacity = _grad_out(st, "opacities", (P, 1), f32)
         has_sh, has_scale = g.shs is not None, g.scales is not None
         # in-place accumulation only when EVERY input gradient of this call lives in the arena
         need = ["means3D", "opacities"] + (["semantics"] if S else []) + (["sh"] if has_sh else ["colors_precomp"]) \
@@ -312,16 +355,16 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors, semantics, scales, 
         acc = int(grad_accumulate and all(n in grad_arena for n in need))
         if grad_accumulate and not acc:
             raise RuntimeError(f"gradient accumulation needs arena slots for {need}")
-        dL_dcov3D = _grad_out("cov3D_precomp", (P, 6), f32) if not has_scale else torch.empty((P, 6), **f32)
+        dL_dcov3D = _grad_out(st, "cov3D_precomp", (P, 6), f32) if not has_scale else torch.empty((P, 6), **f32)
         split = g.shs_rest is not None
         dL_dsh_rest = None
         if split:
-            dL_dsh = _grad_out("sh", (P, 1, 3), f32)
-            dL_dsh_rest = _grad_out("sh_rest", (P, M - 1, 3), f32)
+            dL_dsh = _grad_out(st, "sh", (P, 1, 3), f32)
+            dL_dsh_rest = _grad_out(st, "sh_rest", (P, M - 1, 3), f32)
         else:
-            dL_dsh = _grad_out("sh", (P, M, 3), f32) if has_sh else torch.zeros((P, M, 3), **f32)
-        dL_dscales = _grad_out("scales", (P, 3), f32) if has_scale else torch.zeros((P, 3), **f32)
-        dL_drotations = _grad_out("rotations", (P, 4), f32) if has_scale else torch.zeros((P, 4), **f32)
+            dL_dsh = _grad_out(st, "sh", (P, M, 3), f32) if has_sh else torch.zeros((P, M, 3), **f32)
+        dL_dscales = _grad_out(st, "scales", (P, 3), f32) if has_scale else torch.zeros((P, 3), **f32)
+        dL_drotations = _grad_out(st, "rotations", (P, 4), f32) if has_scale else torch.zeros((P, 4), **f32)
         if P != 0:
             gin = goi_bwd_in(_ptr(gc), _ptr(gs_), _ptr(gd), _ptr(ga), _ptr(alphas), _ptr(radii))
             gout = goi_bwd_out(_ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors),
@@ -471,8 +514,8 @@ def rasterize_gaussians_mask(bg, means3D, colors, semantics, opacity, scales, ro
         stream = _stream(dev)
         R = C.c_int64(0)
         out = goi_fwd_out(_ptr(out_color), _ptr(out_sem), _ptr(out_depth), _ptr(out_alpha), _ptr(radii))
-        global _r_guess
-        bin_bytes = L.goi_binning_bytes(max(int(_r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
+        st = device_state(dev)
+        bin_bytes = L.goi_binning_bytes(max(int(st.r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
         binning = torch.empty((bin_bytes,), **u8)
         args = (C.byref(view), C.byref(g), C.byref(out), C.byref(m), geom.data_ptr(), geom_bytes)
         rc = L.goi_forward_mask(*args, binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, stream, C.byref(R))
@@ -482,7 +525,8 @@ def rasterize_gaussians_mask(bg, means3D, colors, semantics, opacity, scales, ro
             rc = L.goi_forward_mask(*args, binning.data_ptr(), bin_bytes, img.data_ptr(), img_bytes, stream,
                                     C.byref(R))
         _check(rc, "goi_forward_mask")
-        _r_guess = max(R.value, int(0.9 * _r_guess))
+        st.r_guess = max(R.value, int(0.9 * st.r_guess))
+        st.last_num_rendered = int(R.value)
     return out_color, out_sem, out_depth, out_alpha, radii, sim, bgm, idx
 
 

@@ -165,7 +165,10 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
             rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_out_sem, grad_depth,
             grad_alpha, features_dc, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer,
             alpha, rs.debug, raw_flags=_RasterizeGaussiansRaw.RAW, sh_rest=features_rest)
-        grad_dc, grad_rest = grad_sh
+        if isinstance(grad_sh, tuple):
+            grad_dc, grad_rest = grad_sh
+        else:                       # degree-0 model: features_rest is [P,0,3] and travelled as NULL
+            grad_dc, grad_rest = grad_sh, torch.zeros_like(features_rest)
         return (grad_means3D, grad_means2D, grad_dc.view(features_dc.shape), grad_rest.view(features_rest.shape),
                 grad_semantics if semantics.numel() else None, grad_opacities.view(ctx.opacity_shape),
                 grad_scales, grad_rotations, None)

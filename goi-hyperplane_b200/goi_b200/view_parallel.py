@@ -53,23 +53,29 @@ class FlatGradBuffer:
 
 class GradArena:
     """Flat f32 buffer whose slices RECEIVE the rasterizer's parameter gradients directly (the C ABI takes
-    caller-owned output pointers), so one view per rank per step needs neither a zero fill, nor autograd's
-    accumulate-add, nor a packing copy before the all-reduce.
+    caller-owned output pointers), so a view needs neither a zero fill, nor autograd's accumulate-add, nor a
+    packing copy before the all-reduce.
 
     `named_params` maps the binding's gradient names ("means3D", "sh", "semantics", "opacities", "scales",
-    "rotations", ...) to the parameter tensors.  Use as a context manager around the backward call; after it,
-    `p.grad` of every parameter is the arena slice (set `p.grad = None` before each step)."""
+    "rotations", ...) to the parameter tensors.  Use as a context manager around the backward call of EACH view;
+    after it, `p.grad` of every parameter is the arena slice.  Entering the context drops any `.grad` that still
+    aliases the arena from the previous view (otherwise autograd's AccumulateGrad would add the slice to itself),
+    so callers do not have to clear gradients by hand between views.  The arena is installed for the device of its
+    own buffer only (diff_gaussian_rasterization._C keeps one per device); every slot starts on a 16-byte boundary
+    (the padding floats stay zero)."""
+
+    ALIGN = 4                            # floats: slots start 16-byte aligned whatever P is
 
     def __init__(self, named_params: dict):
         self.named = dict(named_params)
         ps = list(self.named.values())
         dev = ps[0].device
-        self.flat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in ps), dtype=torch.float32, device=dev)
         self.slots, off = {}, 0
         for name, p in self.named.items():
             self.slots[name] = self.flat[off:off + p.numel()]
-            off += p.numel()
-
+            off += pad(p.numel())
         self.accumulate = False
 
     def accumulating(self, on: bool = True):
@@ -81,18 +87,21 @@ class GradArena:
 
     def __enter__(self):
         from diff_gaussian_rasterization import _C
-        _C.set_grad_arena(self.slots, accumulate=self.accumulate)
+        self.clear_grads()
+        _C.set_grad_arena(self.slots, accumulate=self.accumulate, device=self.flat.device)
         return self
 
     def __exit__(self, *exc):
         from diff_gaussian_rasterization import _C
-        _C.set_grad_arena(None)
+        _C.set_grad_arena(None, device=self.flat.device)
         self.accumulate = False
         return False
 
     def clear_grads(self):
-        for p in self.named.values():
-            p.grad = None
+        """Drop `.grad`s that alias the arena (done automatically on entering the context, i.e. before each view)."""
+        for name, p in self.named.items():
+            if p.grad is not None and p.grad.data_ptr() == self.slots[name].data_ptr():
+                p.grad = None
 
     def all_reduce(self, async_op: bool = False):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -24,7 +24,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference/submodules/diff-gaussian-rasterization"
 REF_OUT = os.path.join(HERE, "_ref")
-REF_CHANNELS = (1, 10, 16, 32)      # S=0 requests are served by the S=1 build fed with zeros
+REF_CHANNELS = (1, 4, 8, 10, 16, 32)    # S=0 requests are served by the S=1 build fed with zeros
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 

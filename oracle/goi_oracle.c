@@ -20,10 +20,15 @@
  *
  * Parity pin: the reference ships no tests / golden vectors,
  * so this oracle is pinned against (1) the reference's own CUDA core compiled
- * for sm_100a from /root/reference (oracle/_ref, see oracle/build_ref.py) on a
- * B200 -- tests/test_reference_pin.py and the vectors under tests/golden/ that
- * run produced -- and (2) the reference's Python twins eval_sh /
- * build_covariance_from_scaling_rotation (tests/golden/make_twin_vectors.py).
+ * for sm_100a from /root/reference (oracle/_ref, recipe: oracle/build.py) on a
+ * B200 -- live in tests/test_gpu_parity.py::test_oracle_pinned_by_reference_cuda
+ * and through the vectors under tests/golden/ref_*.npz that
+ * tests/golden/make_reference_golden.py produced there (checked on the CPU by
+ * tests/test_oracle_golden.py); (2) the reference's Python twins eval_sh /
+ * build_covariance_from_scaling_rotation (tests/golden/make_twin_vectors.py);
+ * (3) for the mask path, vectors produced by the reference's own
+ * gui/main.py:363-385 + ext/vision_language_align.py:109-122 + networks.py +
+ * scene/semantic_model.py (tests/golden/make_mask_golden.py -> mask_*.npz).
  */
 #include <math.h>
 #include <stdint.h>

@@ -11,7 +11,7 @@
  * of torch tensors) and zero-fills outputs and gradients exactly where that
  * glue does (:69-73, :252-262), so timing it includes the reference's host
  * work and fills.  Uses: pinning the CPU oracle against the real reference
- * kernels on a B200 (tests/test_reference_pin.py, tests/golden/), the GPU
+ * kernels on a B200 (tests/golden/make_reference_golden.py, tests/test_gpu_parity.py), the GPU
  * parity tests, and bench.py --impl reference.
  */
 #include <cuda_runtime.h>

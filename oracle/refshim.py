@@ -9,7 +9,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _libs: dict[int, C.CDLL] = {}
-BUILT_CHANNELS = (1, 10, 16, 32)
+BUILT_CHANNELS = (1, 4, 8, 10, 16, 32)
 
 
 def available(S: int) -> bool:

@@ -46,6 +46,6 @@ for _ in range(10):
     step()
 e1.record()
 torch.cuda.synchronize()
-print(json.dumps({"n_big": n_big, "scale_factor": factor, "num_rendered": _C.last_num_rendered,
+print(json.dumps({"n_big": n_big, "scale_factor": factor, "num_rendered": _C.num_rendered(),
                   "ms_per_view": round(e0.elapsed_time(e1) / 10, 3),
                   "stages_ms": {k: round(v, 4) for k, v in _C.timing_read().items()}}))

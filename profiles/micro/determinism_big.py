@@ -18,7 +18,7 @@ c = collections.Counter(); ref = None; nd = 0
 with torch.no_grad():
     for i in range(60):
         out = render(cam, g, PipeFlags(), bg)
-        c[_C.last_num_rendered] += 1
+        c[_C.num_rendered()] += 1
         if ref is None: ref = out["render"].clone()
         else: nd += int(not torch.equal(ref, out["render"]))
 print(dict(c), "image mismatches", nd)

@@ -50,6 +50,6 @@ for _ in range(10):
     step()
 e1.record()
 torch.cuda.synchronize()
-print(json.dumps({"fraction_moved": frac, "band": band, "num_rendered": _C.last_num_rendered,
+print(json.dumps({"fraction_moved": frac, "band": band, "num_rendered": _C.num_rendered(),
                   "ms_per_view": round(e0.elapsed_time(e1) / 10, 3),
                   "stages_ms": {k: round(v, 4) for k, v in _C.timing_read().items()}}))

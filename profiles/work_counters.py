@@ -37,11 +37,11 @@ for fn in (L.goi_debug_work_fwd, L.goi_debug_work_bwd):
 out = render(cam, g, PipeFlags(), bg)
 torch.autograd.backward([out[k] for k in outs], [w[k] for k in outs])
 torch.cuda.synchronize()
-res = {"config": cfg, "P": P, "W": W, "H": H, "S": S, "num_rendered": _C.last_num_rendered}
+res = {"config": cfg, "P": P, "W": W, "H": H, "S": S, "num_rendered": _C.num_rendered()}
 for name, fn, base in (("fwd", L.goi_debug_work_fwd, 0), ("bwd", L.goi_debug_work_bwd, 4)):
     fn(buf, 0)
     t, walk, anyhit, pairs = (int(buf[base + i]) for i in range(4))
     res[name] = {"cull_tests": t, "warp_walks": walk, "walks_with_hit": anyhit, "blend_pairs": pairs,
                  "lane_efficiency": round(pairs / (32.0 * max(anyhit, 1)), 4),
-                 "walks_per_instance": round(walk / max(_C.last_num_rendered, 1), 3)}
+                 "walks_per_instance": round(walk / max(_C.num_rendered(), 1), 3)}
 print(json.dumps(res))

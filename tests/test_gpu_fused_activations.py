@@ -56,6 +56,43 @@ def test_fused_equals_reference_call_form(P, W, H, S, seed):
         assert err <= 1e-3 * scale, f"dL/d{k}: {err / scale:.3e} of max"
 
 
+@pytest.mark.parametrize("P,W,H,S,seed", [(10_000, 256, 256, 16, 11), (4_033, 160, 112, 7, 12)])
+def test_fused_matches_oracle_on_activated_parameters(P, W, H, S, seed):
+    """Independent check of the fused path: the CPU oracle renders the ACTIVATED parameters (torch CPU sigmoid / exp /
+    normalize / cat of the stored ones), and its gradients are pulled back to the stored parameters through those
+    same torch CPU activations -- no CUDA code on the comparison side."""
+    import numpy as np
+    import common
+    c, cam, bg = _cloud(P, W, H, S, seed)
+    w = make_loss_weights(S, W, H, seed, device="cuda")
+    fus_out, fus_g = _run(c, cam, bg, w, True, S)
+
+    raw = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in c.parameters().items()}
+    act = dict(xyz=raw["xyz"], opacity=torch.sigmoid(raw["opacity"]), scaling=torch.exp(raw["scaling"]),
+               rotation=torch.nn.functional.normalize(raw["rotation"]),
+               features=torch.cat((raw["f_dc"], raw["f_rest"]), dim=1), semantics=raw["semantics"])
+    from goi_b200.scenes import SyntheticGaussians
+    ga = SyntheticGaussians(*[act[k].detach().contiguous() for k in ("xyz", "opacity", "scaling", "rotation", "features",
+                                                                     "semantics")])
+    ora = common.run_oracle(ga, cam.to("cpu"), bg.cpu(), {k: v.cpu() for k, v in w.items()})
+    # ceil(3 sqrt(lambda)) may flip where exp / normalize differ by an ulp between torch-CPU and the fused kernel
+    assert (common.to_np(fus_out["radii"]) != ora["radii"]).mean() < 1e-4
+    got = dict(color=fus_out["render"], semantics=fus_out["semantics"], depth=fus_out["depth"], alpha=fus_out["alpha"])
+    common.assert_images_close(got, ora, max_bad_frac=3e-4, what="fused activations vs oracle")
+    og = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in ora["grads"].items()}
+    torch.autograd.backward(
+        [act["xyz"], act["opacity"], act["scaling"], act["rotation"], act["features"], act["semantics"]],
+        [og["dL_dmeans3D"], og["dL_dopacity"].view_as(act["opacity"]), og["dL_dscales"], og["dL_drotations"],
+         og["dL_dsh"].view_as(act["features"]), og["dL_dsemantics"]])
+    for k, t in raw.items():
+        ref = t.grad
+        scale = float(ref.abs().max()) or 1.0
+        err = float((fus_g[k].cpu() - ref).abs().max())
+        assert err <= 2e-3 * scale, f"dL/d{k}: {err / scale:.3e} of max vs oracle"
+    scale = float(np.abs(ora["grads"]["dL_dmeans2D"]).max())
+    assert float((fus_g["means2D"].cpu() - og["dL_dmeans2D"]).abs().max()) <= 2e-3 * scale
+
+
 def test_fused_rejects_non_default_pipeline():
     c, cam, bg = _cloud(500, 64, 48, 4, 5)
     with pytest.raises(ValueError):

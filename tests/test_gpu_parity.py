@@ -103,9 +103,37 @@ def test_large_splats_match_reference_cuda(n_big, factor):
     assert_images_close(cu, ref, max_bad_frac=0.0, what="large splats vs reference cuda")
     assert_grads_close(cu["grads"], ref["grads"], what="large splats vs reference cuda")
     from diff_gaussian_rasterization import _C
-    r1 = _C.last_num_rendered
+    r1 = _C.num_rendered()
     run_cuda(g, cam, bg)
-    assert _C.last_num_rendered == r1
+    assert _C.num_rendered() == r1
+
+
+@pytest.mark.parametrize("aspect,angle_deg", [(200.0, 45.0), (1000.0, 45.0), (300.0, 30.0), (500.0, 135.0)])
+def test_needle_splats_match_reference_cuda(aspect, angle_deg):
+    """Very elongated diagonal splats: the three products of `power` reach 1e4..1e6 and cancel, so float rounding of
+    the bound in goi_cull.cuh is proportional to their magnitude (its slack scales with it).  A pair the reference
+    blends at alpha ~ 1/255 must not be culled at tile or warp level: instance-for-instance the images, gradients and
+    radii must equal the reference kernels'."""
+    S, P, W, H, seed = 16, 20_000, 640, 400, 13
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    n = 4000
+    with torch.no_grad():
+        # needles in the image plane: long axis x, rotated about the view axis z by angle_deg
+        a = math.radians(angle_deg) * (1.0 + 0.02 * torch.randn(n, generator=torch.Generator().manual_seed(1)))
+        g._rotation[:n] = torch.stack([torch.cos(a / 2), torch.zeros(n), torch.zeros(n), torch.sin(a / 2)], dim=1)
+        s = g._scaling[:n, 1:2] * 0.3
+        g._scaling[:n] = torch.cat([s * aspect, s, s], dim=1)
+        g._opacity[:n] = 0.02 + 0.1 * g._opacity[:n]              # faint: the 1/255 cut runs through the splat
+    bg = torch.tensor([0.2, 0.1, 0.4])
+    w = make_loss_weights(S, W, H, seed)
+    ref = run_reference_cuda(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert torch.equal(cu["radii"].cpu(), ref["radii"].cpu())
+    assert int((cu["radii"][:n] > 200).sum()) > n // 10           # the needles really are hundreds of pixels long
+    assert_images_close(cu, ref, max_bad_frac=0.0, what="needle splats vs reference cuda")
+    assert_grads_close(cu["grads"], ref["grads"], what="needle splats vs reference cuda")
 
 
 def test_dense_skewed_scene_matches_reference_cuda():
@@ -232,10 +260,150 @@ def test_mark_visible_and_trace():
                        scales=g.get_scaling.numpy(), rotations=g.get_rotation.numpy(), img_sem=img_sem.numpy(), **ca)
     assert np.abs(color.cpu().numpy() - exp["color"]).max() <= 1e-4
     # counts are integers: exact except for pairs whose alpha sits on the 0.005 / (1/255) thresholds
-    diff = np.abs(num_gsem.cpu().numpy() - exp["num_gsem"])
-    assert (diff > 0).mean() < 2e-3
-    rel = np.abs(gau_sem.cpu().numpy() - exp["gau_sem"]).max() / max(np.abs(exp["gau_sem"]).max(), 1e-9)
-    assert rel < 2e-2
+    cnt, ecnt = num_gsem.cpu().numpy(), exp["num_gsem"]
+    flipped = cnt != ecnt
+    assert flipped.mean() < 2e-3
+    # rows without a threshold flip: a sum of <= a few hundred float atomics against the oracle's sequential sum
+    got, want = gau_sem.cpu().numpy()[~flipped], exp["gau_sem"][~flipped]
+    err = np.abs(got - want).max(axis=1)
+    tol = 1e-5 * (np.abs(want).max(axis=1) + 1.0)
+    assert (err > tol).mean() < 1e-3, f"{(err > tol).sum()} of {err.size} rows off by more than 1e-5 relative"
+    # a flipped pair moves a row by one img_sem value (<= 1) per channel
+    assert np.abs(gau_sem.cpu().numpy()[flipped] - exp["gau_sem"][flipped]).max(initial=0.0) <= 3.0
+
+
+# ---------------------------------------------------------------------------------------------
+# (b') CUDA vs the reference's own CUDA kernels at the FULL sizes BASELINE.json quotes (configs 2-5)
+# ---------------------------------------------------------------------------------------------
+FULL_SIZE = [
+    ("c2", 1_000_000, 1600, 1000, 16, 1),          # the headline metric's config
+    ("c3", 1_000_000, 800, 600, 32, 2),
+    ("c5_4", 1_000_000, 1280, 720, 4, 4),
+    ("c5_8", 1_000_000, 1280, 720, 8, 4),
+    ("c5_16", 1_000_000, 1280, 720, 16, 4),
+    ("c5_32", 1_000_000, 1280, 720, 32, 4),
+]
+
+
+@pytest.mark.parametrize("name,P,W,H,S,seed", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_cuda_matches_reference_cuda(name, P, W, H, S, seed):
+    """Same bounds as test_cuda_matches_reference_cuda -- radii equal, images <= 1e-4 with ZERO bad pixels, gradients
+    <= 1e-3 of the tensor's max -- on the scenes bench.py times (same generator, same seed, same first camera)."""
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    w = make_loss_weights(S, W, H, seed)
+    ref = run_reference_cuda(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert torch.equal(cu["radii"].cpu(), ref["radii"].cpu()), "radii differ from the reference kernels"
+    rep = assert_images_close(cu, ref, max_bad_frac=0.0, what=f"{name}: cuda vs reference cuda")
+    grep = assert_grads_close(cu["grads"], ref["grads"], what=f"{name}: cuda vs reference cuda")
+    from diff_gaussian_rasterization import _C
+    print("\n", name, "instances: ours", _C.num_rendered(), "reference", ref["num_rendered"], "\n",
+          {k: f"{v['linf']:.2e}" for k, v in rep.items()}, "\n", {k: f"{v['rel']:.2e}" for k, v in grep.items()})
+
+
+def test_full_size_c4_view_matches_reference_cuda():
+    """BASELINE config 4: 5M Gaussians, 1920x1080, S=16, orbit cameras -- one of the 64 views against the reference."""
+    from goi_b200.scenes import make_orbit_scene
+    P, W, H, S = 5_000_000, 1920, 1080, 16
+    if not _ref_ok(S):
+        pytest.skip("oracle/_ref not built")
+    g, cams, bg = make_orbit_scene(P, W, H, S, 64, 3)
+    w = make_loss_weights(S, W, H, 3)
+    cam = cams[5]
+    ref = run_reference_cuda(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert torch.equal(cu["radii"].cpu(), ref["radii"].cpu())
+    assert_images_close(cu, ref, max_bad_frac=0.0, what="c4 view vs reference cuda")
+    assert_grads_close(cu["grads"], ref["grads"], what="c4 view vs reference cuda")
+
+
+def test_full_size_c5_64_matches_oracle():
+    """S=64 at the config-5 size: the reference does not build at this width (its backward needs 76.8 KB of static
+    shared memory), so the check is against the CPU oracle: threshold flips counted."""
+    P, W, H, S, seed = 1_000_000, 1280, 720, 64, 4
+    g, cam, bg = make_scene(P, W, H, S, seed)
+    w = make_loss_weights(S, W, H, seed)
+    ora = run_oracle(g, cam, bg, w)
+    cu = run_cuda(g, cam, bg, w)
+    assert np.array_equal(to_np(cu["radii"]), ora["radii"])
+    assert_images_close(cu, ora, max_bad_frac=2e-4, what="c5_64 vs oracle")
+    assert_grads_close(cu["grads"], ora["grads"], rtol=2e-3, what="c5_64 vs oracle")
+
+
+# ---------------------------------------------------------------------------------------------
+# the C ABI's other forward entry points: goi_forward (allocator callbacks -- the form INTEGRATION.md section B
+# binds) and the two-phase goi_forward_prepare / goi_forward_render
+# ---------------------------------------------------------------------------------------------
+def test_callback_and_two_phase_forward_equal_forward_auto():
+    import ctypes as C
+    from diff_gaussian_rasterization import _C
+    P, W, H, S = 20_000, 333, 207, 16
+    g, cam, bg = make_scene(P, W, H, S, 61)
+    g, cam, bg = g.to("cuda"), cam.to("cuda"), torch.tensor([0.3, 0.1, 0.2], device="cuda")
+    base = run_cuda(g, cam, bg)
+    L = _C.lib()
+    keep = []
+    gs, _ = _C._make_gaussians(g.get_xyz, g.get_features, None, g.get_semantics, g.get_opacity, g.get_scaling,
+                               g.get_rotation, None, keep)
+    view = _C._make_view(bg, cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
+                         math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), 1.0, 3, False, False, keep)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def outputs():
+        f = dict(dtype=torch.float32, device="cuda")
+        o = dict(color=torch.full((3, H, W), float("nan"), **f), semantics=torch.full((S, H, W), float("nan"), **f),
+                 depth=torch.full((1, H, W), float("nan"), **f), alpha=torch.full((1, H, W), float("nan"), **f),
+                 radii=torch.full((P,), -7, dtype=torch.int32, device="cuda"))
+        return o, _C.goi_fwd_out(o["color"].data_ptr(), o["semantics"].data_ptr(), o["depth"].data_ptr(),
+                                 o["alpha"].data_ptr(), o["radii"].data_ptr())
+
+    def same(o):
+        for k in ("color", "semantics", "depth", "alpha", "radii"):
+            assert torch.equal(o[k], base[k]), k
+
+    # (1) goi_forward: the library asks the caller for its three scratch blobs through callbacks
+    sizes = {"g": [], "b": [], "i": []}
+    stores = {"g": [], "b": [], "i": []}
+
+    def mk(tag):
+        def alloc(_user, nbytes):
+            sizes[tag].append(int(nbytes))
+            t = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device="cuda")
+            stores[tag].append(t)
+            return t.data_ptr()
+        return _C.ALLOC_FN(alloc)
+    cbs = {t: mk(t) for t in "gbi"}
+    o, fo = outputs()
+    R = C.c_int64(0)
+    _C._check(L.goi_forward(C.byref(view), C.byref(gs), C.byref(fo), cbs["g"], None, cbs["b"], None, cbs["i"], None,
+                            stream, C.byref(R)), "goi_forward")
+    torch.cuda.synchronize()
+    same(o)
+    assert R.value == _C.num_rendered() and R.value > 0
+    assert sizes["g"] == [L.goi_geom_bytes(P, S)] and sizes["i"] == [L.goi_image_bytes(W, H)]
+    assert sizes["b"] == [L.goi_binning_bytes(R.value)]          # sized from the exact instance count
+
+    # (2) prepare -> (caller sizes the binning blob) -> render
+    o, fo = outputs()
+    geom = torch.empty((L.goi_geom_bytes(P, S),), dtype=torch.uint8, device="cuda")
+    img = torch.empty((L.goi_image_bytes(W, H),), dtype=torch.uint8, device="cuda")
+    R2 = C.c_int64(0)
+    _C._check(L.goi_forward_prepare(C.byref(view), C.byref(gs), o["radii"].data_ptr(), geom.data_ptr(), geom.numel(),
+                                    stream, C.byref(R2)), "goi_forward_prepare")
+    assert R2.value == R.value
+    binning = torch.empty((L.goi_binning_bytes(R2.value),), dtype=torch.uint8, device="cuda")
+    _C._check(L.goi_forward_render(C.byref(view), C.byref(gs), C.byref(fo), geom.data_ptr(), geom.numel(),
+                                   binning.data_ptr(), binning.numel(), img.data_ptr(), img.numel(), R2.value, stream),
+              "goi_forward_render")
+    torch.cuda.synchronize()
+    same(o)
+    # an undersized binning blob is reported, not overrun
+    rc = L.goi_forward_render(C.byref(view), C.byref(gs), C.byref(fo), geom.data_ptr(), geom.numel(),
+                              binning.data_ptr(), 1024, img.data_ptr(), img.numel(), R2.value, stream)
+    assert rc == -3 and b"binning" in L.goi_last_error()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -301,11 +469,14 @@ def test_full_size_payload_linearity_and_euler(big_scene):
 # ---------------------------------------------------------------------------------------------
 # gradient accumulation over views (goi_bwd_out.accumulate): the in-place sum the all-reduce operates on
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("use_sh,use_cov,S", [(True, False, 16), (False, True, 5), (True, False, 0)])
-def test_accumulate_mode_sums_views_in_place(use_sh, use_cov, S):
-    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+@pytest.mark.parametrize("use_sh,use_cov,S,P", [(True, False, 16, 5000), (False, True, 5, 5000), (True, False, 0, 5000),
+                                                 (True, False, 16, 5003), (True, False, 7, 4999)])
+def test_accumulate_mode_sums_views_in_place(use_sh, use_cov, S, P):
+    """P % 4 != 0: gradient slots of a flat buffer start at arbitrary float offsets unless padded; GradArena pads
+    them, and the second half of the test hands the library deliberately MISALIGNED slots (odd float offsets)."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
     from goi_b200 import view_parallel as vp
-    P, W, H = 5000, 160, 112
+    W, H = 160, 112
     g, cam0, bg = make_scene(P, W, H, S, 21)
     g = g.to("cuda")
     bg = bg.cuda()
@@ -354,3 +525,23 @@ def test_accumulate_mode_sums_views_in_place(use_sh, use_cov, S):
         scale = float(expected[k].abs().max()) or 1.0
         err = float((arena.slots[k].view_as(expected[k]) - expected[k]).abs().max())
         assert err <= 1e-4 * scale, f"{k}: accumulated gradient differs by {err / scale:.2e} of max"
+        assert arena.slots[k].data_ptr() % 16 == 0, f"{k}: arena slot not 16-byte aligned"
+    # the C ABI takes any 4-byte-aligned output pointer: slots packed back to back at ODD float offsets
+    flat = torch.full((sum(p.numel() for p in params.values()) + len(params) + 1,), float("nan"), device="cuda")
+    slots, off = {}, 1
+    for k, p in params.items():
+        slots[k] = flat[off:off + p.numel()]
+        off += p.numel() + (1 if (off + p.numel()) % 2 == 0 else 0)      # keep every start odd
+    assert all(t.data_ptr() % 16 != 0 for t in slots.values())
+    for v, (cam, w) in enumerate(zip(cams, ws)):
+        for p in params.values():
+            p.grad = None
+        _C.set_grad_arena(slots, accumulate=v > 0)
+        try:
+            one_view(cam, w)
+        finally:
+            _C.set_grad_arena(None)
+    for k in params:
+        scale = float(expected[k].abs().max()) or 1.0
+        err = float((slots[k].view_as(expected[k]) - expected[k]).abs().max())
+        assert err <= 1e-4 * scale, f"{k} (misaligned slot): {err / scale:.2e} of max"
