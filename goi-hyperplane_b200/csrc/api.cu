@@ -94,7 +94,6 @@ static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 256)
 
 GeomState carve_geom(char* base, int P, int S)
 {
-    (void)S;
     GeomState g{};
     char* c = base;
     const size_t Pn = (size_t)(P > 0 ? P : 1);
@@ -113,6 +112,8 @@ GeomState carve_geom(char* base, int P, int S)
     obtain(c, g.sortp_temp, g.sortp_temp_bytes);
     obtain(c, g.rect, Pn);
     obtain(c, g.dopacity, Pn);
+    g.grad_row_floats = bwd_row_floats(S);
+    obtain(c, g.grad_rows, Pn * (size_t)(g.grad_row_floats > 0 ? g.grad_row_floats : 1));
     g.scan_temp_bytes = scan_temp_bytes_for(P);
     obtain(c, g.scan_temp, g.scan_temp_bytes);
     g.total_bytes = (size_t)(c - base) + 256;
@@ -413,21 +414,27 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
     // accumulators of the composite backward (everything else is fully written by k_preprocess_bwd)
     // (in accumulate mode the arrays that ARE input gradients keep their contents: the atomics add to them)
     const bool acc = out->accumulate != 0;
-    stage_begin(ST_ZERO, st);
-    GOI_CUDA(cudaMemsetAsync(out->dL_dmean2D, 0, sizeof(float) * 3 * P, st), "zero grads");
-    GOI_CUDA(cudaMemsetAsync(out->dL_dconic, 0, sizeof(float) * 4 * P, st), "zero grads");
-    // raw (logit) opacities: the composite accumulates dL/d(sigmoid) of THIS view in the geometry blob and
-    // k_preprocess_bwd applies sigmoid' while writing / adding to dL_dopacity
     const bool raw_op = (g->raw_flags & GOI_RAW_OPACITY) != 0;
     goi_bwd_out o2 = *out;
-    if (raw_op) {
-        o2.dL_dopacity = gs.dopacity;
-        GOI_CUDA(cudaMemsetAsync(gs.dopacity, 0, sizeof(float) * P, st), "zero grads");
-    } else if (!acc) GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
-    if (!acc || g->colors_precomp == nullptr)
-        GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
-    GOI_CUDA(cudaMemsetAsync(out->dL_ddepth, 0, sizeof(float) * P, st), "zero grads");
-    if (g->S > 0 && !acc) GOI_CUDA(cudaMemsetAsync(out->dL_dsemantic, 0, sizeof(float) * (size_t)g->S * P, st), "zero grads");
+    stage_begin(ST_ZERO, st);
+    if (gs.grad_row_floats > 0) {
+        // S <= 16: one scratch row per Gaussian is the composite's only accumulator; k_preprocess_bwd unpacks it into
+        // dL_dmean2D / dL_dconic / dL_dopacity / dL_dcolor / dL_ddepth / dL_dsemantic (adding where `accumulate` says so)
+        GOI_CUDA(cudaMemsetAsync(gs.grad_rows, 0, sizeof(float) * (size_t)gs.grad_row_floats * P, st), "zero grads");
+    } else {
+        GOI_CUDA(cudaMemsetAsync(out->dL_dmean2D, 0, sizeof(float) * 3 * P, st), "zero grads");
+        GOI_CUDA(cudaMemsetAsync(out->dL_dconic, 0, sizeof(float) * 4 * P, st), "zero grads");
+        // raw (logit) opacities: the composite accumulates dL/d(sigmoid) of THIS view in the geometry blob and
+        // k_preprocess_bwd applies sigmoid' while writing / adding to dL_dopacity
+        if (raw_op) {
+            o2.dL_dopacity = gs.dopacity;
+            GOI_CUDA(cudaMemsetAsync(gs.dopacity, 0, sizeof(float) * P, st), "zero grads");
+        } else if (!acc) GOI_CUDA(cudaMemsetAsync(out->dL_dopacity, 0, sizeof(float) * P, st), "zero grads");
+        if (!acc || g->colors_precomp == nullptr)
+            GOI_CUDA(cudaMemsetAsync(out->dL_dcolor, 0, sizeof(float) * 3 * P, st), "zero grads");
+        GOI_CUDA(cudaMemsetAsync(out->dL_ddepth, 0, sizeof(float) * P, st), "zero grads");
+        if (g->S > 0 && !acc) GOI_CUDA(cudaMemsetAsync(out->dL_dsemantic, 0, sizeof(float) * (size_t)g->S * P, st), "zero grads");
+    }
     stage_end(ST_ZERO, st);
 
     if (num_rendered > 0) {

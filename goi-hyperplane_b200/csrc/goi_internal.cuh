@@ -38,6 +38,9 @@ struct GeomState {
     size_t    sortp_temp_bytes;
     uint2*    rect;              // [P]
     float*    dopacity;          // [P]   dL/d(activated opacity) of one view when opacities are raw logits
+    float*    grad_rows;         // [P][grad_row_floats] per-Gaussian accumulators of the composite backward (S <= 16):
+                                 //       payload gradients + six pixel moments, see k_composite_bwd_mma
+    int       grad_row_floats;   // 0 = the direct-atomics backward is used for this channel count
     Meta*     meta;
     char*     scan_temp;
     size_t    scan_temp_bytes;
@@ -62,6 +65,9 @@ GeomState    carve_geom(char* base, int P, int S);
 ImageState   carve_image(char* base, int W, int H);
 BinningState carve_binning(char* base, int64_t R);
 
+inline int sem_groups(int S);
+// floats per scratch row of the tensor-core composite backward: 8 x (payload tiles + 1 moment tile); 0 for S > 16
+inline int bwd_row_floats(int S);
 inline int sem_groups(int S) {           // float4 groups the composite kernels are instantiated for
     if (S <= 0) return 0;
     if (S <= 4) return 1;
@@ -70,6 +76,11 @@ inline int sem_groups(int S) {           // float4 groups the composite kernels 
     if (S <= 16) return 4;
     if (S <= 32) return 8;
     return 16;
+}
+inline int bwd_row_floats(int S) {
+    const int ns4 = sem_groups(S);
+    if (ns4 > 4) return 0;
+    return 8 * ((4 + 4 * ns4 + 7) / 8 + 1);
 }
 
 // ---- measurement hooks (process-wide, mutex-guarded: autograd's backward runs on another thread; api.cu) -----

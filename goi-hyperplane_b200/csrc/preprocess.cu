@@ -494,8 +494,24 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
 // Per-Gaussian backward: d(conic) -> d(cov2D) -> d(cov3D), d(mean) through the EWA Jacobian, the
 // projection, the depth and the SH view direction; d(cov3D) -> d(scale), d(quaternion).
 // ------------------------------------------------------------------------------------------------
+// Scratch rows of the tensor-core composite backward (k_composite_bwd_mma): per Gaussian 8 NT floats = the payload
+// gradients (r, g, b, depth, semantics) and the six pixel moments (M0, Mx, My, Mxx, Mxy, Myy) about rint(mean2D);
+// logical column c = 8 nt + n lives at float 2 NT (n >> 1) + 2 nt + (n & 1).  rows == NULL: the composite wrote
+// dL_dmean2D / dL_dconic / dL_dcolor / dL_ddepth / opacity itself (direct-atomics kernel, S > 16).
+struct GradRows {
+    const float* rows;
+    int rowf, nt;
+    int W, H, S;
+    float* out_mean2D;       // [P,3]  API outputs the composite used to accumulate itself
+    float* out_conic;        // [P,4]
+    float* out_color;        // [P,3]
+    float* out_depth;        // [P]
+    float* out_sem;          // [P,S]
+    int acc_color, acc_sem;  // add to (instead of overwrite) the arrays that are parameter gradients
+};
+
 __global__ void __launch_bounds__(128) k_preprocess_bwd(
-    int P, int D, int M, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
+    GradRows gr, int P, int D, int M, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
     const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
     const float* __restrict__ rotations, float scale_modifier, const float* __restrict__ cov3Ds,
     const float* __restrict__ view, const float* __restrict__ proj, const float* __restrict__ campos,
@@ -520,6 +536,72 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
     const int base = blockIdx.x * blockDim.x + warp * 32;
     const int rows = max(0, min(32, P - base));
 
+    // ---- composite-level gradients of this Gaussian: from the scratch row (moments -> mean2D / conic / opacity),
+    //      or from the arrays the direct-atomics composite filled
+    float in_g2x = 0.f, in_g2y = 0.f, in_depth = 0.f, in_dopa = 0.f;
+    float3 in_conic = make_float3(0.f, 0.f, 0.f);
+    float in_rgb[3] = {0.f, 0.f, 0.f};
+    if (gr.rows != nullptr) {
+        const int rowf = gr.rowf, NT2 = 2 * gr.nt;
+        if (rows > 0) {                                 // 32 x rowf contiguous floats -> padded tile (coalesced)
+            const float4* src4 = reinterpret_cast<const float4*>(gr.rows + (size_t)base * rowf);
+            const int n4 = rows * rowf / 4;
+            for (int f = lane; f < n4; f += 32) {
+                const float4 v = src4[f];
+                const int e = 4 * f;
+                float* d = tile + (e / rowf) * PRE_ROWSTRIDE + (e % rowf);
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+        __syncwarp();
+        auto phys = [NT2](int c) { const int nt = c >> 3, n = c & 7; return NT2 * (n >> 1) + 2 * nt + (n & 1); };
+        if (active) {
+            const float* row = tile + lane * PRE_ROWSTRIDE;
+            in_rgb[0] = row[phys(0)]; in_rgb[1] = row[phys(1)]; in_rgb[2] = row[phys(2)];
+            in_depth = row[phys(3)];
+            const int mc = 8 * (gr.nt - 1);
+            const float M0 = row[phys(mc)], Mx = row[phys(mc + 1)], My = row[phys(mc + 2)];
+            const float Mxx = row[phys(mc + 3)], Mxy = row[phys(mc + 4)], Myy = row[phys(mc + 5)];
+            const float4 q0 = geo[2 * (size_t)idx], q1 = geo[2 * (size_t)idx + 1];     // (mx, my, A, B), (C, o, ..)
+            const float fx = q0.x - rintf(q0.x), fy = q0.y - rintf(q0.y);             // d = f - l', l' = pixel - rint(mean)
+            const float sx = fx * M0 - Mx, sy = fy * M0 - My;                          // sum u dx, sum u dy
+            const float sxx = fmaf(fx, fmaf(fx, M0, -2.f * Mx), Mxx);
+            const float syy = fmaf(fy, fmaf(fy, M0, -2.f * My), Myy);
+            const float sxy = fmaf(fx * fy, M0, Mxy) - fx * My - fy * Mx;
+            // backward.cu:602-621 summed over the pixels: dG/ddel = -G (A dx + B dy, C dy + B dx), u = dL/dG * G
+            in_g2x = -(q0.z * sx + q0.w * sy) * (0.5f * (float)gr.W);
+            in_g2y = -(q1.x * sy + q0.w * sx) * (0.5f * (float)gr.H);
+            in_conic = make_float3(-0.5f * sxx, -0.5f * sxy, -0.5f * syy);
+            in_dopa = q1.y > 0.f ? M0 / q1.y : 0.f;                                    // sum G dL/dalpha = sum u / opacity
+        }
+        if (in_range) {
+            gr.out_mean2D[3 * idx] = in_g2x; gr.out_mean2D[3 * idx + 1] = in_g2y; gr.out_mean2D[3 * idx + 2] = 0.f;
+            gr.out_conic[4 * idx] = in_conic.x; gr.out_conic[4 * idx + 1] = in_conic.y; gr.out_conic[4 * idx + 2] = 0.f;
+            gr.out_conic[4 * idx + 3] = in_conic.z;
+            gr.out_depth[idx] = in_depth;
+            if (gr.out_color) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    gr.out_color[3 * idx + c] = gr.acc_color ? gr.out_color[3 * idx + c] + in_rgb[c] : in_rgb[c];
+            }
+        }
+        if (gr.out_sem != nullptr && gr.S > 0 && (!gr.acc_sem || __any_sync(0xffffffffu, active))) {
+            const int S = gr.S;                         // [32 x S] contiguous in the output: coalesced
+            float* dst = gr.out_sem + (size_t)base * S;
+            for (int i = lane; i < rows * S; i += 32) {
+                const float v = tile[(i / S) * PRE_ROWSTRIDE + phys(4 + i % S)];
+                dst[i] = gr.acc_sem ? dst[i] + v : v;
+            }
+        }
+        __syncwarp();                                   // the tile is reused for the SH rows below
+    } else if (active) {
+        in_g2x = dL_dmean2D[3 * idx]; in_g2y = dL_dmean2D[3 * idx + 1];
+        in_conic = make_float3(dL_dconics[4 * idx], dL_dconics[4 * idx + 1], dL_dconics[4 * idx + 3]);
+        in_depth = dL_ddepth[idx];
+        in_rgb[0] = dL_dcolor[3 * idx]; in_rgb[1] = dL_dcolor[3 * idx + 1]; in_rgb[2] = dL_dcolor[3 * idx + 2];
+        if (dopa_act != nullptr) in_dopa = dopa_act[idx];
+    }
+
     if (shs != nullptr && __any_sync(0xffffffffu, active)) {
         if (shs_rest) sh_tile_load_split(tile, shs + (size_t)base * 3, shs_rest + (size_t)base * (rowlen - 3), rows, M, lane);
         else sh_tile_load(tile, shs + (size_t)base * rowlen, rows, rowlen, lane);
@@ -535,7 +617,7 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
         float c3[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) c3[i] = cov3Ds[6 * idx + i];
-        const float3 dL_dconic = make_float3(dL_dconics[4 * idx], dL_dconics[4 * idx + 1], dL_dconics[4 * idx + 3]);
+        const float3 dL_dconic = in_conic;
         Cov2DSetup cs = cov2d_setup(mean, h_x, h_y, tan_fovx, tan_fovy, c3, view);
         const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
         const float x_grad_mul = cs.txtz < -limx || cs.txtz > limx ? 0 : 1;
@@ -599,14 +681,14 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
         const float m_w = 1.0f / (m_hom.w + 0.0000001f);
         const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
         const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-        const float g2x = dL_dmean2D[3 * idx], g2y = dL_dmean2D[3 * idx + 1];
+        const float g2x = in_g2x, g2y = in_g2y;
         float3 dm;
         dm.x = (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
         dm.y = (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
         dm.z = (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
         gmean.x += dm.x; gmean.y += dm.y; gmean.z += dm.z;
 
-        const float gdepth = dL_ddepth[idx];
+        const float gdepth = in_depth;
         const float mul3 = view[2] * mean.x + view[6] * mean.y + view[10] * mean.z + view[14];
         float3 dm2;
         dm2.x = (view[2] - view[3] * mul3) * gdepth;
@@ -628,7 +710,7 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
             const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
             const float* sh = row;
             const uint8_t cl = clamped[idx];
-            dRGB[0] = dL_dcolor[3 * idx]; dRGB[1] = dL_dcolor[3 * idx + 1]; dRGB[2] = dL_dcolor[3 * idx + 2];
+            dRGB[0] = in_rgb[0]; dRGB[1] = in_rgb[1]; dRGB[2] = in_rgb[2];
             dRGB[0] *= (cl & 1) ? 0 : 1;
             dRGB[1] *= (cl & 2) ? 0 : 1;
             dRGB[2] *= (cl & 4) ? 0 : 1;
@@ -714,12 +796,16 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
         }
     }
     if (!in_range) return;
-    if (dopa_act != nullptr) {
-        // raw opacities: d sigmoid(x)/dx = o (1 - o); the composite left dL/do of this view in dopa_act
+    if (raw_flags & GOI_RAW_OPACITY) {
+        // raw opacities: d sigmoid(x)/dx = o (1 - o); in_dopa = dL/do of this view
         float v = 0.f;
-        if (active) { const float o = geo[2 * (size_t)idx + 1].y; v = dopa_act[idx] * (o * (1.f - o)); }
+        if (active) { const float o = geo[2 * (size_t)idx + 1].y; v = in_dopa * (o * (1.f - o)); }
         if (!acc) dL_dopacity[idx] = v;
         else if (active) dL_dopacity[idx] += v;
+    } else if (gr.rows != nullptr) {
+        // (the direct-atomics composite accumulates activated-opacity gradients into dL_dopacity itself)
+        if (!acc) dL_dopacity[idx] = in_dopa;
+        else if (active) dL_dopacity[idx] += in_dopa;
     }
     if (acc) {
         if (!active) return;                  // zero contribution
@@ -799,8 +885,17 @@ cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, con
     const float focal_y = v.height / (2.0f * v.tan_fovy);
     const float focal_x = v.width / (2.0f * v.tan_fovx);
     const float* cov3D_ptr = g.cov3D_precomp ? g.cov3D_precomp : gs.cov3D;    // rasterizer_impl.cu:579
+    GradRows gr{};
+    if (gs.grad_row_floats > 0) {
+        gr.rows = gs.grad_rows; gr.rowf = gs.grad_row_floats; gr.nt = gs.grad_row_floats / 8;
+        gr.W = v.width; gr.H = v.height; gr.S = g.S;
+        gr.out_mean2D = out.dL_dmean2D; gr.out_conic = out.dL_dconic; gr.out_color = out.dL_dcolor;
+        gr.out_depth = out.dL_ddepth; gr.out_sem = out.dL_dsemantic;
+        gr.acc_color = out.accumulate != 0 && g.colors_precomp != nullptr;
+        gr.acc_sem = out.accumulate != 0;
+    }
     k_preprocess_bwd<<<(P + 127) / 128, 128, 0, st>>>(
-        P, v.sh_degree, g.M, g.means3D, in.radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
+        gr, P, v.sh_degree, g.M, g.means3D, in.radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
         cov3D_ptr, v.viewmatrix, v.projmatrix, v.cam_pos, focal_x, focal_y, v.tan_fovx, v.tan_fovy,
         out.dL_dmean2D, out.dL_dconic, out.dL_dcolor, out.dL_ddepth,
         out.dL_dmean3D, out.dL_dcov3D, g.shs ? out.dL_dsh : nullptr,

@@ -87,7 +87,7 @@ class GradArena:
 
     def __enter__(self):
         from diff_gaussian_rasterization import _C
-        self.clear_grads()
+        self.clear_grads(only_aliased=True)
         _C.set_grad_arena(self.slots, accumulate=self.accumulate, device=self.flat.device)
         return self
 
@@ -97,10 +97,11 @@ class GradArena:
         self.accumulate = False
         return False
 
-    def clear_grads(self):
-        """Drop `.grad`s that alias the arena (done automatically on entering the context, i.e. before each view)."""
+    def clear_grads(self, only_aliased: bool = False):
+        """Set `.grad = None` on the arena's parameters.  Entering the context does this for the gradients that alias
+        the arena (i.e. before each view); call it yourself once per step if other code left ordinary `.grad`s."""
         for name, p in self.named.items():
-            if p.grad is not None and p.grad.data_ptr() == self.slots[name].data_ptr():
+            if p.grad is not None and (not only_aliased or p.grad.data_ptr() == self.slots[name].data_ptr()):
                 p.grad = None
 
     def all_reduce(self, async_op: bool = False):
