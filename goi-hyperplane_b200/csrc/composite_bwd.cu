@@ -815,7 +815,7 @@ struct BwdWarp {
     static constexpr int FG = 80, FT = 20, FRAG_FLOATS = 8 * FG;        // A-fragment order of (w, u), see BwdMma
     static constexpr int NQW = 4 * NKQ;                    // packed lo words of the Q image   (8 NKQ values)
     static constexpr int NRW = 4 * NTP;                    // packed lo words of the R image   (8 NTP values)
-    static constexpr int LOS = ((NQW + NRW + 3) / 4) * 4 + 4;            // per-lane word stride: = 4 or 12 or 20 or 28 mod 32
+    static constexpr int LOS = ((NQW + NRW + 7) / 8) * 8 + 4;            // per-lane word stride: 4 x odd = conflict-free LDS.128
     static constexpr int RING = 64;
     // per-warp shared memory, in floats
     static constexpr int OFF_GEO = 0;                                  // [2][CH][8]
@@ -967,7 +967,7 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
         for (int k = 0; k < C::NQW + C::NRW; ++k) sts_u32(aLo + 4 * k, lo_words[k]);
         // staged payload rows: floats [0, NPROD) are written by cp.async (4 + S of them), [NPROD] = 1 (dL/dalpha
         // column), everything else must read as zero
-        for (int i = lane; i < 2 * CH * PRS; i += 32) sts32(aPay + 4 * i, (i % PRS) == NPROD ? 1.f : 0.f);
+        for (int f = 4 + S; f < PRS; ++f) sts32(aPay + 4 * (lane * PRS + f), f == NPROD ? 1.f : 0.f);      // lane = one of the 2 x 16 rows
         __syncwarp();
     }
     // Mom[p][m], m = gid: 1, lx, ly, lx^2, lx ly, ly^2 (0 for m = 6, 7) at pixel p = 8 tig + 2 ks + h -> lx = 2 ks + h, ly = tig
@@ -1027,14 +1027,18 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
         const uint32_t gdst = aGeo + buf * (CH * 32), pdst = aPay + buf * (CH * PRS * 4);
         if (lane < c) sts_u32(aLidx + 4 * (buf * CH + lane), lds_u32(aRing + 4 * (C::RING + ((head + lane) & (C::RING - 1)))));
         if (sem_vec || NS4 == 0) {
-            constexpr int PARTS = 3 + NS4;              // 16-byte pieces per record: g0, g1, rgbd, semantic float4s
-            const int S4 = S >> 2;
-            for (int piece = lane; piece < c * PARTS; piece += 32) {
-                const int w = piece / PARTS, part = piece - w * PARTS;
-                const uint32_t id = lds_u32(aRing + 4 * ((head + w) & (C::RING - 1)));
-                if (part < 2) cp_async16_s(gdst + w * 32 + part * 16, &geo[2 * (size_t)id + part]);
-                else if (part == 2) cp_async16_s(pdst + w * (PRS * 4), &rgbd[id]);
-                else if (part - 3 < S4) cp_async16_s(pdst + w * (PRS * 4) + 16 + (part - 3) * 16, sem + (size_t)id * S + 4 * (part - 3));
+            // one lane per record: 3 + S/4 sixteen-byte copies (geometry x2, rgb+depth, semantic float4s)
+            if (lane < c) {
+                const uint32_t id = lds_u32(aRing + 4 * ((head + lane) & (C::RING - 1)));
+                const float4* gsrc = geo + 2 * (size_t)id;
+                const uint32_t pd = pdst + lane * (PRS * 4);
+                cp_async16_s(gdst + lane * 32, gsrc);
+                cp_async16_s(gdst + lane * 32 + 16, gsrc + 1);
+                cp_async16_s(pd, rgbd + id);
+                const float* ssrc = sem + (size_t)id * S;
+#pragma unroll
+                for (int k = 0; k < NS4; ++k)
+                    if (4 * k < S) cp_async16_s(pd + 16 + 16 * k, ssrc + 4 * k);
             }
         } else {                                        // semantic rows that are not float4-addressable: 4-byte copies
             for (int w = 0; w < c; ++w) {
@@ -1087,17 +1091,28 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
                     bh[nt][0] = tf32_hi(b.x); bh[nt][1] = tf32_hi(b.y);
                     bl[nt][0] = tf32_lo(b.x, bh[nt][0]); bl[nt][1] = tf32_lo(b.y, bh[nt][1]);
                 }
+                // (consecutive MMAs go to different accumulators: the dependent one is four issues away)
+                uint32_t ql[2][4];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint32_t w0 = qlo[(mt * NKQ + ks) * 2], w1 = qlo[(mt * NKQ + ks) * 2 + 1];
-                    const uint32_t l0 = w0 << 16, l1 = w0 & 0xffff0000u, l2 = w1 << 16, l3 = w1 & 0xffff0000u;
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        mma_tf32_16x8x8(accq[mt][nt], l0, l1, l2, l3, bh[nt][0], bh[nt][1]);
-                        mma_tf32_16x8x8(accq[mt][nt], qhi[mt][ks][0], qhi[mt][ks][1], qhi[mt][ks][2], qhi[mt][ks][3], bl[nt][0], bl[nt][1]);
-                        mma_tf32_16x8x8(accq[mt][nt], qhi[mt][ks][0], qhi[mt][ks][1], qhi[mt][ks][2], qhi[mt][ks][3], bh[nt][0], bh[nt][1]);
-                    }
+                    ql[mt][0] = w0 << 16; ql[mt][1] = w0 & 0xffff0000u; ql[mt][2] = w1 << 16; ql[mt][3] = w1 & 0xffff0000u;
                 }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        mma_tf32_16x8x8(accq[mt][nt], ql[mt][0], ql[mt][1], ql[mt][2], ql[mt][3], bh[nt][0], bh[nt][1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        mma_tf32_16x8x8(accq[mt][nt], qhi[mt][ks][0], qhi[mt][ks][1], qhi[mt][ks][2], qhi[mt][ks][3], bl[nt][0], bl[nt][1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        mma_tf32_16x8x8(accq[mt][nt], qhi[mt][ks][0], qhi[mt][ks][1], qhi[mt][ks][2], qhi[mt][ks][3], bh[nt][0], bh[nt][1]);
             }
             // c0, c1: pixel gid + 16 mt, walks 2 tig + 8 nt (+1); c2, c3: pixel gid + 8 + 16 mt.
             // slot of (walk i, pixel p) = (i & 7) FG + (p >> 3) FT + ((p & 7) >> 1) 4 + (i >> 3) + 2 (p & 1)
@@ -1182,23 +1197,25 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const float4 a = lds128(fragW + 16 * ks);           // (a0, a1, a2, a3) of this k-step
+                    const float4 b = lds128(fragU + 16 * ks);
                     const uint32_t h0 = tf32_hi(a.x), h1 = tf32_hi(a.y), h2 = tf32_hi(a.z), h3 = tf32_hi(a.w);
                     const uint32_t l0 = tf32_lo(a.x, h0), l1 = tf32_lo(a.y, h1), l2 = tf32_lo(a.z, h2), l3 = tf32_lo(a.w, h3);
+                    const uint32_t uh0 = tf32_hi(b.x), uh1 = tf32_hi(b.y), uh2 = tf32_hi(b.z), uh3 = tf32_hi(b.w);
+                    const uint32_t ul0 = tf32_lo(b.x, uh0), ul1 = tf32_lo(b.y, uh1), ul2 = tf32_lo(b.z, uh2), ul3 = tf32_lo(b.w, uh3);
+                    // small terms first; consecutive MMAs go to different accumulators
+#pragma unroll
+                    for (int nt = 0; nt < NTP; ++nt)
+                        mma_tf32_16x8x8(accp[nt], l0, l1, l2, l3, rhi[nt][ks][0], rhi[nt][ks][1]);
+                    mma_tf32_16x8x8(accm, ul0, ul1, ul2, ul3, bmom[ks][0], bmom[ks][1]);
 #pragma unroll
                     for (int nt = 0; nt < NTP; ++nt) {
                         const uint32_t wd = rlo[nt * 4 + ks];
-                        mma_tf32_16x8x8(accp[nt], l0, l1, l2, l3, rhi[nt][ks][0], rhi[nt][ks][1]);      // small terms first
                         mma_tf32_16x8x8(accp[nt], h0, h1, h2, h3, wd << 16, wd & 0xffff0000u);
-                        mma_tf32_16x8x8(accp[nt], h0, h1, h2, h3, rhi[nt][ks][0], rhi[nt][ks][1]);
                     }
-                }
+                    mma_tf32_16x8x8(accm, uh0, uh1, uh2, uh3, bmom[ks][0], bmom[ks][1]);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const float4 a = lds128(fragU + 16 * ks);
-                    const uint32_t h0 = tf32_hi(a.x), h1 = tf32_hi(a.y), h2 = tf32_hi(a.z), h3 = tf32_hi(a.w);
-                    const uint32_t l0 = tf32_lo(a.x, h0), l1 = tf32_lo(a.y, h1), l2 = tf32_lo(a.z, h2), l3 = tf32_lo(a.w, h3);
-                    mma_tf32_16x8x8(accm, l0, l1, l2, l3, bmom[ks][0], bmom[ks][1]);
-                    mma_tf32_16x8x8(accm, h0, h1, h2, h3, bmom[ks][0], bmom[ks][1]);
+                    for (int nt = 0; nt < NTP; ++nt)
+                        mma_tf32_16x8x8(accp[nt], h0, h1, h2, h3, rhi[nt][ks][0], rhi[nt][ks][1]);
                 }
             }
             // ---------------- epilogue: rows gid (c0, c1) and gid + 8 (c2, c3) of the chunk ----------------
