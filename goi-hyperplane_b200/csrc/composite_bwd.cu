@@ -878,16 +878,49 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
 
-    // pixel state
+    // pixel state.  Every global load of the prologue is issued before the first use of any of them (the warp
+    // lives for ~100k cycles; four serialised DRAM round trips were 10 % of that)
     const uint32_t last_contributor = inside ? n_contrib[pix] : 0;
+    const float oa = inside ? out_alpha[pix] : 1.f;
+    const uint2 range = ranges[tile];
+    float g_rgb[3] = {0.f, 0.f, 0.f}, g_depth = 0.f, g_alpha = 0.f;
+    float g_sem[NSF];
+#pragma unroll
+    for (int i = 0; i < NSF; ++i) g_sem[i] = 0.f;
+    if (inside) {
+        if (dL_dpix) { g_rgb[0] = dL_dpix[pix]; g_rgb[1] = dL_dpix[HW + pix]; g_rgb[2] = dL_dpix[2 * HW + pix]; }
+        if (dL_dpixsem) {
+#pragma unroll
+            for (int ch = 0; ch < 4 * NS4; ++ch)
+                if (ch < S) g_sem[ch] = dL_dpixsem[ch * HW + pix];
+        }
+        if (dL_dpixdepth) g_depth = dL_dpixdepth[pix];
+        if (dL_dpixalpha) g_alpha = dL_dpixalpha[pix];
+    }
+    const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
     uint32_t nmax = last_contributor;                  // this block only walks entries [0, max n_contrib of its pixels)
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
     if (nmax == 0) return;                             // (warp-uniform; no block-level synchronisation anywhere)
     const int n = (int)nmax;
-    const uint2 range = ranges[tile];
 
-    const float T_final = inside ? (1 - out_alpha[pix]) : 0;
+    // ---- list scan state: entries n-1, n-2, ... 0; group g covers list indices n-1-32g-lane.  The (cull word,
+    //      Gaussian index) pairs of the next PF groups are always in flight.
+    constexpr int PF = 3;
+    uint32_t pf_cull[PF], pf_id[PF];
+    auto prefetch_group = [&](int p, uint32_t& c, uint32_t& id) {
+        const int idx = n - 1 - p - lane;
+        c = 0; id = 0;
+        if (idx >= 0) {
+            const uint32_t li = range.x + (uint32_t)idx;
+            c = __ldg(cull + li);
+            id = __ldg(point_list + li);
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < PF; ++k) prefetch_group(32 * k, pf_cull[k], pf_id[k]);
+
+    const float T_final = 1.f - oa;
     float T = T_final;
     float nTf_bg;
     const uint32_t aGeo = sbase + C::OFF_GEO * 4, aPay = sbase + C::OFF_PAY * 4, aW = sbase + C::OFF_W * 4,
@@ -899,21 +932,7 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     //      8 ks + 2 tig + h), R image (B operand, k-index = pixel 8 tig + 2 ks + h, column = channel 8 nt + gid).
     uint32_t qhi[2][NKQ][4], rhi[NTP][4][2];
     {
-        float g_rgb[3] = {0.f, 0.f, 0.f}, g_depth = 0.f, g_alpha = 0.f;
-        float g_sem[NSF];
-#pragma unroll
-        for (int i = 0; i < NSF; ++i) g_sem[i] = 0.f;
-        if (inside) {
-            if (dL_dpix) { g_rgb[0] = dL_dpix[pix]; g_rgb[1] = dL_dpix[HW + pix]; g_rgb[2] = dL_dpix[2 * HW + pix]; }
-            if (dL_dpixsem) {
-#pragma unroll
-                for (int ch = 0; ch < 4 * NS4; ++ch)
-                    if (ch < S) g_sem[ch] = dL_dpixsem[ch * HW + pix];
-            }
-            if (dL_dpixdepth) g_depth = dL_dpixdepth[pix];
-            if (dL_dpixalpha) g_alpha = dL_dpixalpha[pix];
-        }
-        nTf_bg = -T_final * (bg[0] * g_rgb[0] + bg[1] * g_rgb[1] + bg[2] * g_rgb[2]);
+        nTf_bg = -T_final * (bg0 * g_rgb[0] + bg1 * g_rgb[1] + bg2 * g_rgb[2]);
         // transpose through the (still unused) W/U region: scratch[c][pixel], 36 floats per row
 #pragma unroll
         for (int pv = 0; pv <= NPROD; ++pv) {
@@ -976,9 +995,11 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            // m = gid -> lx^a ly^b: (a, b) = (0,0) (1,0) (0,1) (2,0) (1,1) (0,2); m = 6, 7 -> 0   (two bits per entry)
             const float lx = (float)(2 * ks + h), ly = (float)tig;
-            const float mv = gid == 0 ? 1.f : gid == 1 ? lx : gid == 2 ? ly : gid == 3 ? lx * lx : gid == 4 ? lx * ly :
-                             gid == 5 ? ly * ly : 0.f;
+            const int a = (0x184 >> (2 * gid)) & 3, b = (0x910 >> (2 * gid)) & 3;
+            const float fx = (a >= 1 ? lx : 1.f) * (a == 2 ? lx : 1.f), fy = (b >= 1 ? ly : 1.f) * (b == 2 ? ly : 1.f);
+            const float mv = gid < 6 ? fx * fy : 0.f;
             bmom[ks][h] = __float_as_uint(mv);
         }
 
@@ -990,26 +1011,17 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     float* const my_rows = rows + 2 * NT * tig;
     GOI_STAT_DECL;
 
-    // ---- list scan state: entries n-1, n-2, ... 0; group `pos` covers list indices n-1-pos-lane
     int pos = 0;
     uint32_t head = 0, tail = 0;                        // survivor ring (warp-uniform counters)
-    uint32_t pf_cull = 0, pf_id = 0;
-    auto prefetch_group = [&](int p) {
-        const int idx = n - 1 - p - lane;
-        if (p < n && idx >= 0) {
-            const uint32_t li = range.x + (uint32_t)idx;
-            pf_cull = __ldg(cull + li);
-            pf_id = __ldg(point_list + li);
-        }
-    };
-    prefetch_group(0);
     auto fill_ring = [&]() {                            // scan until 16 survivors are queued or the list ends
         while (tail - head < (uint32_t)CH && pos < n) {
             const int idx = n - 1 - pos - lane;
-            const bool keep = idx >= 0 && ((pf_cull >> warp) & 1u);
-            const uint32_t id = pf_id;
+            const bool keep = idx >= 0 && ((pf_cull[0] >> warp) & 1u);
+            const uint32_t id = pf_id[0];
+#pragma unroll
+            for (int k = 0; k + 1 < PF; ++k) { pf_cull[k] = pf_cull[k + 1]; pf_id[k] = pf_id[k + 1]; }
             pos += 32;
-            prefetch_group(pos);
+            prefetch_group(pos + 32 * (PF - 1), pf_cull[PF - 1], pf_id[PF - 1]);
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             GOI_STAT_ADD(0, idx >= 0 ? 1u : 0u);
             if (keep) {
@@ -1143,21 +1155,25 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
             oc = g1.y;
             hitc = (lidx < last_contributor) && !(power > 0.0f) && !(power < g1.z) && !(alphac < 1.0f / 255.0f);
         }
+        // geometry records are read two walks ahead of their use, q one walk ahead (shared-memory latency off the chain)
+        float4 g0 = lds128(geo_s + 32), g1 = lds128(geo_s + 48);
+        float q = lds32(pubU);
 #pragma unroll 2
         for (int i = 0; i < ccnt; ++i) {
             // A(i+1): backward.cu:527-542 (behind this pixel's last contributor, the two skips) and power_cut
-            const int in = min(i + 1, CH - 1);
-            const float4 g0 = lds128(geo_s + in * 32), g1 = lds128(geo_s + in * 32 + 16);
+            const int in = min(i + 1, CH - 1), in2 = min(i + 2, CH - 1);
+            const float4 g0n = lds128(geo_s + in2 * 32), g1n = lds128(geo_s + in2 * 32 + 16);
+            const float qn = lds32(pubU + (uint32_t)((in & 7) * (C::FG * 4) + (in >> 3) * 4));
             const uint32_t lidx = __shfl_sync(0xffffffffu, lidx_reg, in);
             const float dx = g0.x - pxf, dy = g0.y - pyf;
             const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
             const float Gn = expf(power);
             const float alphan = fminf(0.99f, g1.y * Gn);
             const bool hitn = (lidx < last_contributor) && !(power > 0.0f) && !(power < g1.z) && !(alphan < 1.0f / 255.0f);
+            const float on = g1.y;
             // B(i), branch-free: a rejected lane is a Gaussian of alpha 0 / G 0 (inv = 1, T unchanged, weight 0; the
             // (acc, last_q, last_alpha) recurrence stays exact: the next step computes 0 * last_q + 1 * acc)
             const uint32_t po = (uint32_t)((i & 7) * (C::FG * 4) + (i >> 3) * 4);
-            const float q = lds32(pubU + po);
             const unsigned hm = __ballot_sync(0xffffffffu, hitc);
             rowmask |= (hm != 0u ? 1u : 0u) << i;
             GOI_STAT_ADD(2, (lane == 0 && hm) ? 1u : 0u);
@@ -1173,7 +1189,8 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
             const float dL_dopa = fmaf(nTf_bg, inv, (q - acc) * T);
             sts32(pubW + po, a_eff * T);
             sts32(pubU + po, (oc * dL_dopa) * Gh);      // u = dL/dG * G
-            Gc = Gn; alphac = alphan; oc = g1.y; hitc = hitn;
+            Gc = Gn; alphac = alphan; oc = on; hitc = hitn;
+            g0 = g0n; g1 = g1n; q = qn;
         }
         if (rowmask != 0) {                             // (warp-uniform) something blended in this chunk
             for (int r = ccnt; r < CH; ++r) {           // rows of a partial chunk must read as zero

@@ -586,12 +586,19 @@ __global__ void __launch_bounds__(128) k_preprocess_bwd(
             }
         }
         if (gr.out_sem != nullptr && gr.S > 0 && (!gr.acc_sem || __any_sync(0xffffffffu, active))) {
-            const int S = gr.S;                         // [32 x S] contiguous in the output: coalesced
+            // [32 x S] contiguous floats in the output.  S <= 16 here (rows exist only for S <= 16): 32 / SP Gaussians per
+            // pass, SP = S rounded up to a power of two, so no per-element division
+            const int S = gr.S;
+            const int sp_log = S <= 1 ? 0 : 32 - __clz(S - 1), SP = 1 << sp_log;
+            const int ch = lane & (SP - 1), rsub = lane >> sp_log, rstep = 32 >> sp_log;
+            const int col = phys(4 + ch);
             float* dst = gr.out_sem + (size_t)base * S;
-            for (int i = lane; i < rows * S; i += 32) {
-                const float v = tile[(i / S) * PRE_ROWSTRIDE + phys(4 + i % S)];
-                dst[i] = gr.acc_sem ? dst[i] + v : v;
-            }
+            if (ch < S)
+                for (int r = rsub; r < rows; r += rstep) {
+                    const float v = tile[r * PRE_ROWSTRIDE + col];
+                    float* d = dst + r * S + ch;
+                    *d = gr.acc_sem ? *d + v : v;
+                }
         }
         __syncwarp();                                   // the tile is reused for the SH rows below
     } else if (active) {
