@@ -1158,8 +1158,7 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
         // geometry records are read two walks ahead of their use, q one walk ahead (shared-memory latency off the chain)
         float4 g0 = lds128(geo_s + 32), g1 = lds128(geo_s + 48);
         float q = lds32(pubU);
-#pragma unroll 2
-        for (int i = 0; i < ccnt; ++i) {
+        auto walk = [&](const int i) {
             // A(i+1): backward.cu:527-542 (behind this pixel's last contributor, the two skips) and power_cut
             const int in = min(i + 1, CH - 1), in2 = min(i + 2, CH - 1);
             const float4 g0n = lds128(geo_s + in2 * 32), g1n = lds128(geo_s + in2 * 32 + 16);
@@ -1191,6 +1190,12 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
             sts32(pubU + po, (oc * dL_dopa) * Gh);      // u = dL/dG * G
             Gc = Gn; alphac = alphan; oc = on; hitc = hitn;
             g0 = g0n; g1 = g1n; q = qn;
+        };
+        if (ccnt == CH) {                               // full chunk (all but a block's last): compile-time walk indices
+#pragma unroll
+            for (int i = 0; i < CH; ++i) walk(i);
+        } else {
+            for (int i = 0; i < ccnt; ++i) walk(i);
         }
         if (rowmask != 0) {                             // (warp-uniform) something blended in this chunk
             for (int r = ccnt; r < CH; ++r) {           // rows of a partial chunk must read as zero
