@@ -139,6 +139,8 @@ BinningState carve_binning(char* base, int64_t R)
     obtain(c, b.keys[1], Rn);
     obtain(c, b.vals[0], Rn);
     obtain(c, b.vals[1], Rn);
+    b.cull_plane = (Rn + 255) & ~(size_t)255;
+    obtain(c, b.cull8, 8 * b.cull_plane);
     b.sort_temp_bytes = sort_temp_bytes_for(R);
     obtain(c, b.sort_temp, b.sort_temp_bytes);
     b.total_bytes = (size_t)(c - base) + 256;
@@ -327,7 +329,8 @@ static int forward_render_impl(const goi_view* view, const goi_gaussians* g, con
     {
         StageScope sc(ST_COMPOSITE_FWD, st);
         if (mask) GOI_CUDA(launch_composite_fwd_mask(*view, *g, *out, *mask, gs, bs.vals[0], bs.vals[1], is, st), "composite forward + mask");
-        else GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], is, st), "composite forward");
+        else GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], gs.grad_row_floats > 0 ? bs.cull8 : nullptr,
+                                           bs.cull_plane, is, st), "composite forward");
     }
     return debug_sync(view, st, "composite forward");
 }
@@ -439,7 +442,8 @@ int goi_backward(const goi_view* view, const goi_gaussians* g, int64_t num_rende
 
     if (num_rendered > 0) {
         StageScope sc(ST_COMPOSITE_BWD, st);
-        GOI_CUDA(launch_composite_bwd(*view, *g, *in, o2, gs, bs.vals[0], bs.vals[1], is, st), "composite backward");
+        GOI_CUDA(launch_composite_bwd(*view, *g, *in, o2, gs, bs.vals[0], bs.vals[1], bs.cull8, bs.cull_plane, is, st),
+                 "composite backward");
     }
     if ((rc = debug_sync(view, st, "composite backward")) != GOI_OK) return rc;
     { StageScope sc(ST_PREPROCESS_BWD, st); GOI_CUDA(launch_preprocess_bwd(*view, *g, *in, *out, gs, st), "preprocess backward"); }

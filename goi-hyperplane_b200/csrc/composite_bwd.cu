@@ -851,7 +851,8 @@ __device__ __forceinline__ uint32_t pack_lo(float a, float b) { return (__float_
 template <int NS4>
 __global__ void __launch_bounds__(32, 16)
 k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
-                     const uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cull, int W, int H, int gx,
+                     const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ cull8, size_t cull_plane,
+                     int W, int H, int gx,
                      const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
                      int S, int sem_vec, const float* __restrict__ bg, const float* __restrict__ out_alpha,
                      const uint32_t* __restrict__ n_contrib,
@@ -907,13 +908,14 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     // ---- list scan state: entries n-1, n-2, ... 0; group g covers list indices n-1-32g-lane.  The (cull word,
     //      Gaussian index) pairs of the next PF groups are always in flight.
     constexpr int PF = 3;
+    const uint8_t* const my_cull = cull8 + (size_t)warp * cull_plane;
     uint32_t pf_cull[PF], pf_id[PF];
     auto prefetch_group = [&](int p, uint32_t& c, uint32_t& id) {
         const int idx = n - 1 - p - lane;
         c = 0; id = 0;
         if (idx >= 0) {
             const uint32_t li = range.x + (uint32_t)idx;
-            c = __ldg(cull + li);
+            c = __ldg(my_cull + li);                    // this block's verdict plane (k_composite_fwd_warp)
             id = __ldg(point_list + li);
         }
     };
@@ -1016,7 +1018,7 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     auto fill_ring = [&]() {                            // scan until 16 survivors are queued or the list ends
         while (tail - head < (uint32_t)CH && pos < n) {
             const int idx = n - 1 - pos - lane;
-            const bool keep = idx >= 0 && ((pf_cull[0] >> warp) & 1u);
+            const bool keep = idx >= 0 && pf_cull[0] != 0u;
             const uint32_t id = pf_id[0];
 #pragma unroll
             for (int k = 0; k + 1 < PF; ++k) { pf_cull[k] = pf_cull[k + 1]; pf_id[k] = pf_id[k + 1]; }
@@ -1282,8 +1284,8 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
 
 template <int NS4>
 static cudaError_t launch_bwd_warp_t(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
-                                     const GeomState& gs, const uint32_t* point_list, const uint32_t* cull,
-                                     const ImageState& is, cudaStream_t st)
+                                     const GeomState& gs, const uint32_t* point_list, const uint8_t* cull8,
+                                     size_t cull_plane, const ImageState& is, cudaStream_t st)
 {
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
     const size_t smem = (size_t)BwdWarp<NS4>::TOTAL * sizeof(float);
@@ -1295,8 +1297,9 @@ static cudaError_t launch_bwd_warp_t(const goi_view& v, const goi_gaussians& g, 
     if (e != cudaSuccess) return e;
     const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
     kern<<<gx * gy * 8, 32, smem, st>>>(
-        is.ranges, is.tile_order, point_list, cull, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S, sem_vec,
-        v.background, in.out_alpha, is.n_contrib, in.dL_dcolor, in.dL_dsemantic, in.dL_ddepth, in.dL_dalpha, gs.grad_rows);
+        is.ranges, is.tile_order, point_list, cull8, cull_plane, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S,
+        sem_vec, v.background, in.out_alpha, is.n_contrib, in.dL_dcolor, in.dL_dsemantic, in.dL_ddepth, in.dL_dalpha,
+        gs.grad_rows);
     count_launches(1);
     return cudaGetLastError();
 }
@@ -1346,16 +1349,17 @@ static cudaError_t launch_bwd_t(const goi_view& v, const goi_gaussians& g, const
 
 cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                  const goi_bwd_out& out, const GeomState& gs, const uint32_t* point_list,
-                                 const uint32_t* cull, const ImageState& is, cudaStream_t st)
+                                 const uint32_t* cull, const uint8_t* cull8, size_t cull_plane, const ImageState& is,
+                                 cudaStream_t st)
 {
     // S <= 16: pixel reductions on the tensor cores into per-Gaussian scratch rows (k_preprocess_bwd unpacks them);
     // wider vectors: the shared-memory reduction with direct atomics
     switch (sem_groups(g.S)) {
-        case 0: return launch_bwd_warp_t<0>(v, g, in, gs, point_list, cull, is, st);
-        case 1: return launch_bwd_warp_t<1>(v, g, in, gs, point_list, cull, is, st);
-        case 2: return launch_bwd_warp_t<2>(v, g, in, gs, point_list, cull, is, st);
-        case 3: return launch_bwd_warp_t<3>(v, g, in, gs, point_list, cull, is, st);
-        case 4: return launch_bwd_warp_t<4>(v, g, in, gs, point_list, cull, is, st);
+        case 0: return launch_bwd_warp_t<0>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
+        case 1: return launch_bwd_warp_t<1>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
+        case 2: return launch_bwd_warp_t<2>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
+        case 3: return launch_bwd_warp_t<3>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
+        case 4: return launch_bwd_warp_t<4>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
         case 8: return launch_bwd_t<8>(v, g, in, out, gs, point_list, cull, is, st);
         default: return launch_bwd_t<16>(v, g, in, out, gs, point_list, cull, is, st);
     }

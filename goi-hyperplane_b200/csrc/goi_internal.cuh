@@ -56,6 +56,8 @@ struct BinningState {
     uint32_t* keys[2];           // double buffer: tile id (instances are emitted in depth order)
     uint32_t* vals[2];           // double buffer: Gaussian index; after the sort [0] = list (copied there if the
                                  // sort ended in [1]), [1] = the forward's per-entry warp-block cull masks
+    uint8_t*  cull8;             // [8][cull_plane] per 8x4 block of a tile: 1 = this list entry may blend there (written by
+    size_t    cull_plane;        //       k_composite_fwd_warp for k_composite_bwd_warp; S <= 16)
     char*     sort_temp;
     size_t    sort_temp_bytes;   // CUB's own answer for this item count (sort_temp_bytes_for)
     size_t    total_bytes;
@@ -109,10 +111,11 @@ size_t sort_temp_bytes_for(int64_t R);
 // forward composite into the dead half of the sort's value double buffer, read back by the backward)
 cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
                                  const GeomState& gs, const uint32_t* point_list, uint32_t* cull_out,
-                                 const ImageState& is, cudaStream_t st);
+                                 uint8_t* cull8, size_t cull_plane, const ImageState& is, cudaStream_t st);
 cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                  const goi_bwd_out& out, const GeomState& gs, const uint32_t* point_list,
-                                 const uint32_t* cull, const ImageState& is, cudaStream_t st);
+                                 const uint32_t* cull, const uint8_t* cull8, size_t cull_plane, const ImageState& is,
+                                 cudaStream_t st);
 cudaError_t launch_preprocess_bwd(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
                                   const goi_bwd_out& out, const GeomState& gs, cudaStream_t st);
 cudaError_t launch_trace(const goi_view& v, const goi_gaussians& g, const float* img_sem, float* out_color,

@@ -133,15 +133,23 @@ def test_fused_mask_epilogue_equals_render_then_mask(S, mode, want_sem):
         sim_ref, idx_ref = hp.compute_similarity(base["semantics"], out_bg_mask=bg_ref, channels_first=True,
                                                  want_idx=True)
     out = render_mask(cam, g, PipeFlags(), bg, hp, want_semantics=want_sem, want_idx=True)
-    assert torch.equal(out["render"], base["render"]) and torch.equal(out["depth"], base["depth"])
+    # The plain render accumulates the payload on the tensor cores (3xTF32), the fused-mask variant with FP32 FMAs:
+    # identical blending decisions (alpha, radii bit-equal), payload sums equal to rounding.
     assert torch.equal(out["alpha"], base["alpha"]) and torch.equal(out["radii"], base["radii"])
-    if want_sem:
-        assert torch.equal(out["semantics"], base["semantics"])
-    else:
+    for k in ("render", "depth") + (("semantics",) if want_sem else ()):
+        assert float((out[k] - base[k]).abs().max()) <= 2e-5 * max(1.0, float(base[k].abs().max())), k
+    if not want_sem:
         assert out["semantics"] is None
-    assert torch.equal(out["idx"].view(-1), idx_ref)
-    assert torch.equal(out["sim"].view(-1), sim_ref)
-    assert torch.equal(out["bg_mask"].view(-1), bg_ref)
+    # the mask of the fused epilogue = goi_mask applied to ITS OWN semantic image, bit for bit
+    if want_sem:
+        bg_own = torch.zeros(H * W, dtype=torch.bool, device="cuda")
+        sim_own, idx_own = hp.compute_similarity(out["semantics"], out_bg_mask=bg_own, channels_first=True, want_idx=True)
+        assert torch.equal(out["idx"].view(-1), idx_own) and torch.equal(out["sim"].view(-1), sim_own)
+        assert torch.equal(out["bg_mask"].view(-1), bg_own)
+    # and equal to the mask of the plain render except at arg-max near-ties (the two semantic images differ by ~1e-6)
+    same = out["idx"].view(-1) == idx_ref
+    assert float(same.float().mean()) > 0.999
+    assert torch.equal(out["sim"].view(-1)[same], sim_ref[same]) and torch.equal(out["bg_mask"].view(-1)[same], bg_ref[same])
     assert out["mask"].shape == (H, W) and 0 < int(out["mask"].sum()) < H * W
     # and against the CPU oracle's mask on the same rendered features
     kw = dict(mode=0, log_scale=0.1, thresh=0.86) if mode == "ape" else dict(mode=1, hyperplane_b=hp.svm_bias, thresh=0.5)
