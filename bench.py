@@ -112,6 +112,29 @@ def make_views(W, H, device):
     return cams
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this rank (and therefore the first-touch placement of its pinned staging buffers) to the CPUs that are local
+    to GPU `index` (sysfs local_cpulist of the GPU's PCI function).  Returns a short description, or None."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(path + "/local_cpulist") as f:
+            spec = f.read().strip()
+        with open(path + "/numa_node") as f:
+            node = int(f.read().strip())
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def build_workload(config, dev):
     """(gaussians, cameras, background) of a config: SURVEY.md section 8d.  c4 is the object-centric orbit scene (64
     cameras on a circle looking at the origin), the others the frustum-filling scene with 8 jittered poses."""
@@ -179,6 +202,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _C.lib()        # hard error if the CUDA library is missing: no fallback path
@@ -259,14 +283,19 @@ def run_ours(args):
     value = world * vps * args.steps / (ms_total / 1e3)
 
     # ---------------- end-to-end arm: per-view inputs from pinned host memory ----------------
-    host_w = [{k: v.cpu().pin_memory() for k, v in make_loss_weights(S, W, H, seed + j).items()} for j in range(2)]
-    h2d_bytes = sum(v.numel() * 4 for v in host_w[0].values()) + (16 + 16 + 3 + 3) * 4
+    # The per-view supervision travels the way a trainer holds it: the RGB map as uint8, the feature / depth / alpha maps
+    # as fp16 (39 B per pixel instead of 84), and is expanded to the f32 loss-weight images on the device.
+    def compact(wd):
+        return {"render": ((wd["render"] + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8),
+                "semantics": wd["semantics"].half(), "depth": wd["depth"].half(), "alpha": wd["alpha"].half()}
+    host_w = [{k: v.cpu().pin_memory() for k, v in compact(make_loss_weights(S, W, H, seed + j)).items()} for j in range(2)]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_w[0].values()) + (16 + 16 + 3 + 3) * 4
     copy_stream = torch.cuda.Stream(device=dev)
-    # ring of NSLOT device slots, copies issued two views ahead: the copy of a view (134 MB, ~2.5-3.3 ms on PCIe 5
-    # x16 while kernels run) then has two view periods to land instead of one
+    # ring of NSLOT device slots, copies issued two views ahead: a view's copy then has two view periods to land
     NSLOT = 3
     slots = [{k: torch.empty_like(v, device=dev) for k, v in host_w[0].items()} for _ in range(NSLOT)]
-    ready = [torch.cuda.Event() for _ in range(NSLOT)]
+    expanded = {k: torch.empty_like(v) for k, v in w_dev.items()}      # f32 images the backward reads (one set: the
+    ready = [torch.cuda.Event() for _ in range(NSLOT)]                 # compute stream expands right before a view)
     freed = [torch.cuda.Event() for _ in range(NSLOT)]
     loss_host = [torch.zeros(2).pin_memory() for _ in range(NSLOT)]
 
@@ -294,7 +323,13 @@ def run_ours(args):
         if v + 2 < n_e2e_views:
             prefetch(view + 2)
         torch.cuda.current_stream().wait_event(ready[view % NSLOT])
-        return slots[view % NSLOT]
+        sl = slots[view % NSLOT]
+        expanded["render"].copy_(sl["render"])
+        expanded["render"].mul_(1.0 / 127.5).sub_(1.0)
+        for k in ("semantics", "depth", "alpha"):
+            expanded[k].copy_(sl[k])
+        freed[view % NSLOT].record()              # the compact slot may now be overwritten by the copy stream
+        return expanded
 
     def view_done(view, out, wv):
         # D2H read of the view's result: the pseudo-loss value and the gradient norm of the semantic field
@@ -303,7 +338,6 @@ def run_ours(args):
             loss = torch.dot(out["semantics"].detach().reshape(-1), wv["semantics"].reshape(-1))   # one pass, no temp
             loss_host[view % NSLOT].copy_(torch.stack([loss, torch.linalg.vector_norm(arena.slots['semantics'])]),
                                           non_blocking=True)
-        freed[view % NSLOT].record()              # the slot may now be overwritten by the copy stream
 
     def e2e_step(i):
         step(i, view_inputs, view_done)
@@ -341,7 +375,11 @@ def run_ours(args):
         "clocks": clocks,
         "ms_per_view": round(ms_total / args.steps / vps, 4),
         "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes * vps,
-                "d2h_bytes_per_step": 8 * vps, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "d2h_bytes_per_step": 8 * vps, "ms_per_step": round(ms_e2e / args.steps, 4),
+                "supervision": "per view from pinned host memory: uint8 RGB + fp16 feature / depth / alpha loss-weight "
+                               "maps (39 B per pixel at S=16), expanded to f32 on the device; camera matrices; the loss "
+                               "and the semantic gradient norm are read back",
+                "host_affinity": affinity},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
