@@ -289,7 +289,7 @@ struct FwdWarp {
     static constexpr int NTC = (NPROD + 7) / 8;            // 8-channel tiles
     static constexpr int CH = 16;                          // walks per chunk = two k-steps
     static constexpr int PRS = 24;                         // floats per staged payload row (>= 8 NTC; conflict-free B loads)
-    static constexpr int RING = 128;                       // queued survivors: geometry 32 B + list index
+    static constexpr int RING = 64;                        // queued survivors (<= 16 in process + 47 pending): geometry 32 B + list index
     static constexpr int WBLK = 160;                       // floats per (m-tile, k-step) block of the w operand
     static constexpr int OFF_RGEO = 0;                                 // [RING][8]
     static constexpr int OFF_RID = OFF_RGEO + RING * 8;                // [RING] Gaussian index
@@ -327,7 +327,7 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v)
 }
 
 template <int NS4>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, 20)
 k_composite_fwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                      const uint32_t* __restrict__ point_list, int W, int H, int gx,
                      const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
@@ -475,10 +475,14 @@ k_composite_fwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
 
         // ---------------- walk phase ----------------
         unsigned anyhit = 0;
+        // geometry records are read two walks ahead of their use (shared-memory latency off the dependency chain)
+        auto rec = [&](int i) { return aRgeo + ((chunk_head + (uint32_t)i) & (RING - 1)) * 32; };
+        float4 ga0 = lds128(rec(0)), ga1 = lds128(rec(0) + 16), gb0 = lds128(rec(1)), gb1 = lds128(rec(1) + 16);
         auto walk = [&](const int i) {
-            const uint32_t slot = (chunk_head + (uint32_t)i) & (RING - 1);
-            const float4 g0 = lds128(aRgeo + slot * 32), g1 = lds128(aRgeo + slot * 32 + 16);
-            const uint32_t lidx = lds_u32f(aRidx + 4 * slot);
+            const float4 g0 = ga0, g1 = ga1;
+            ga0 = gb0; ga1 = gb1;
+            gb0 = lds128(rec(min(i + 2, CH - 1))); gb1 = lds128(rec(min(i + 2, CH - 1)) + 16);
+            const uint32_t lidx = lds_u32f(aRidx + 4 * ((chunk_head + (uint32_t)i) & (RING - 1)));
             const float dx = g0.x - pxf, dy = g0.y - pyf;
             const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
             const float alpha = fminf(0.99f, g1.y * expf(power));
@@ -555,15 +559,20 @@ k_composite_fwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
             const int qx = wx0 + (p & 7), qy = wy0 + (p >> 3);
             if (qx < W && qy < H) {
                 const size_t qpix = (size_t)qy * W + qx;
+                // this lane's first channel of tile nt is 8 nt + 2 tig: one lane-dependent base, compile-time steps of HW
+                float* const sem_base = out_sem + qpix + (ptrdiff_t)(2 * tig - 4) * (ptrdiff_t)HW;
 #pragma unroll
                 for (int nt = 0; nt < NTC; ++nt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int ch = 8 * nt + 2 * tig + h;        // payload value: r, g, b, depth, semantics...
                         const float v = acc[mt][nt][2 * r2 + h];
-                        if (ch < 3) out_color[ch * HW + qpix] = v + Tp * (ch == 0 ? bg0 : ch == 1 ? bg1 : bg2);
-                        else if (ch == 3) out_depth[qpix] = v;
-                        else if (ch - 4 < S) out_sem[(size_t)(ch - 4) * HW + qpix] = v;
+                        if (nt == 0) {                               // r, g | b, depth | semantics 0..3
+                            if (tig == 0) out_color[(size_t)h * HW + qpix] = v + Tp * (h == 0 ? bg0 : bg1);
+                            else if (tig == 1) { if (h == 0) out_color[2 * HW + qpix] = v + Tp * bg2; else out_depth[qpix] = v; }
+                            else if (2 * tig + h - 4 < S) sem_base[(size_t)h * HW] = v;
+                        } else if (8 * nt + 2 * tig + h - 4 < S) {
+                            sem_base[(size_t)(8 * nt + h) * HW] = v;
+                        }
                     }
             }
         }
