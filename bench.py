@@ -172,16 +172,22 @@ def metric_name(config):
     return f"views/sec fwd+bwd @{pm} Gaussians,{W}x{H},{S}ch; HBM GB/s vs roofline"
 
 
-def config_dict(args, world, vps, num_rendered_mean):
-    """`config` of the JSON line -- the SAME key set for both arms (only num_rendered_mean differs in value: this
-    build culls provably empty tile instances, the reference walks its full rectangles)."""
+def config_dict(args, world, vps):
+    """`config` of the JSON line: identical (keys and values) for both arms."""
     P, W, H, S, _ = CONFIGS[args.config]
     return {"workload": f"{args.config}: P={P} Gaussians, {W}x{H}, S={S} semantic channels, SH degree 3, "
                         f"fwd+bwd of all four outputs, {64 if args.config == 'c4' else N_VIEWS} camera poses",
             "views_per_step": world * vps, "views_per_gpu_per_step": vps,
             "parallelism": f"view-dp{world}, one all-reduce of the per-Gaussian gradients per step",
-            "l2_policy": "inputs larger than L2 (300 MB parameters + 98 MB sort buffers per view)",
-            "num_rendered_mean": round(num_rendered_mean)}
+            "l2_policy": "inputs larger than L2 (300 MB parameters + 98 MB sort buffers per view)"}
+
+
+def run_dict(args, num_rendered_mean):
+    """What differs between the arms by construction (kept OUT of `config`, which is identical for both): this build
+    culls provably empty tile instances and does not read the instance count back per view."""
+    return {"num_rendered_mean": round(num_rendered_mean),
+            "host_sync": "per view (num_rendered read-back)" if (args.sync_binning or args.impl == "reference")
+                         else "none per view (instance count stays on the device; status words checked per step)"}
 
 
 def b_comp(R, W, H, S):
@@ -260,8 +266,13 @@ def run_ours(args):
         return float(ms.item())
 
     # ---------------- device-resident arm ----------------
+    step(0, w_dev)                  # (seeds the instance-count estimate through the synchronous path)
+    # training-loop mode: no num_rendered read-back per view (goi_forward_async); every view's status word is examined
+    # -- overflow of the binning capacity would invalidate the run -- when the timed region ends
+    _C.set_async_binning(not args.sync_binning, dev)
     for i in range(args.warmup):
         step(i, w_dev)
+    _C.check_async(dev, wait=True)
     _C.timing_enable(True)
     stage_acc, rs = {}, []
     launches0 = _C.launch_count()
@@ -271,9 +282,11 @@ def run_ours(args):
 
     def resident_step(i):
         step(i, w_dev)
-        rs.append(_C.num_rendered())       # (of the step's last view; the poses differ by a few degrees)
+        _C.check_async(dev, wait=False)    # examines the status words that have already landed; never blocks
+        rs.append(_C.num_rendered())       # (of the most recent examined view; the poses differ by a few degrees)
 
     ms_total = timed(resident_step, args.steps)
+    _C.check_async(dev, wait=True)         # raises if any view of the timed region overflowed its binning capacity
     # per-stage CUDA-event times of the timed region's views (ring of the last 64), read after the region
     for k, v in _C.timing_read().items():
         stage_acc[k] = max(v, 0.0) * args.steps          # mean ms per VIEW x steps
@@ -354,6 +367,7 @@ def run_ours(args):
     if "stages" in _dbg:
         _C.timing_enable(True)
     ms_e2e = timed(e2e_step, args.steps)
+    _C.check_async(dev, wait=True)
     if "stages" in _dbg:
         print("e2e stages", {k: round(v, 4) for k, v in _C.timing_read().items()}, file=sys.stderr)
         _C.timing_enable(False)
@@ -371,7 +385,8 @@ def run_ours(args):
         "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, world, vps, R),
+        "config": config_dict(args, world, vps),
+        "run": run_dict(args, R),
         "clocks": clocks,
         "ms_per_view": round(ms_total / args.steps / vps, 4),
         "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes * vps,
@@ -499,7 +514,8 @@ def run_reference(args):
         "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, world, vps, sum(rs) / max(len(rs), 1)),
+        "config": config_dict(args, world, vps),
+        "run": run_dict(args, sum(rs) / max(len(rs), 1)),
         "clocks": clocks,
         "ms_per_view": round(ms / args.steps / vps, 4),
         "reference_class": "gpu",
@@ -522,6 +538,8 @@ def main():
     ap.add_argument("--views-per-step", type=int, default=4,
                     help="training views per GPU per step (gradients summed in place, one all-reduce per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-binning", action="store_true",
+                    help="read num_rendered back per view like the reference (default: goi_forward_async, no host sync)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

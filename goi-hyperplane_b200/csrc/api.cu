@@ -259,7 +259,7 @@ int goi_forward_prepare(const goi_view* view, const goi_gaussians* g, int32_t* r
     { StageScope sc(ST_SCAN, st); GOI_CUDA(run_scan(gs, g->P, st), "prefix sum"); }
     // the one host sync of the path (reference: cudaMemcpy at rasterizer_impl.cu:285)
     Meta host_meta;
-    GOI_CUDA(cudaMemcpyAsync(&host_meta, gs.meta, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "read num_rendered");
+    GOI_CUDA(cudaMemcpyAsync(&host_meta, gs.meta, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "read num_rendered");
     GOI_CUDA(cudaStreamSynchronize(st), "read num_rendered");
     if (host_meta.prefilter_violation)
         return fail(GOI_ERR_INVALID_ARG, "Point is filtered although prefiltered is set. This shouldn't happen!");
@@ -286,7 +286,7 @@ static int validate_mask(const goi_mask_args* a, bool standalone)
 static int forward_render_impl(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
                                const goi_mask_args* mask, void* geom_buf, size_t geom_bytes, void* binning_buf,
                                size_t binning_bytes, void* image_buf, size_t image_bytes, int64_t num_rendered,
-                               void* stream)
+                               void* stream, bool device_count = false)
 {
     int rc = validate(view, g);
     if (rc != GOI_OK) return rc;
@@ -324,7 +324,7 @@ static int forward_render_impl(const goi_view* view, const goi_gaussians* g, con
     ImageState is = carve_image((char*)image_buf, view->width, view->height);
     BinningState bs = carve_binning((char*)binning_buf, num_rendered);
     int selector = 0;
-    GOI_CUDA(run_binning(*view, g->P, out->radii, gs, bs, is, num_rendered, &selector, st), "binning");
+    GOI_CUDA(run_binning(*view, g->P, out->radii, gs, bs, is, num_rendered, &selector, st, device_count), "binning");
     if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
     {
         StageScope sc(ST_COMPOSITE_FWD, st);
@@ -368,6 +368,33 @@ int goi_forward_auto(const goi_view* view, const goi_gaussians* g, const goi_fwd
         return fail(GOI_ERR_WORKSPACE, "binning buffer too small for %lld instances", (long long)*num_rendered);
     return goi_forward_render(view, g, out, geom_buf, geom_bytes, binning_buf, binning_bytes, image_buf, image_bytes,
                               *num_rendered, stream);
+}
+
+int goi_forward_async(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out, void* geom_buf,
+                      size_t geom_bytes, void* binning_buf, size_t binning_bytes, int64_t capacity, void* image_buf,
+                      size_t image_bytes, void* stream, uint32_t* status_host)
+{
+    int rc = validate(view, g);
+    if (rc != GOI_OK) return rc;
+    if (!out || !status_host) return fail(GOI_ERR_INVALID_ARG, "out / status_host is NULL");
+    if (capacity <= 0 || capacity >= ((int64_t)1 << 31)) return fail(GOI_ERR_INVALID_ARG, "capacity must be in [1, 2^31)");
+    if (g->P == 0) {
+        status_host[0] = status_host[1] = status_host[2] = 0; status_host[3] = (uint32_t)capacity;
+        return forward_render_impl(view, g, out, nullptr, geom_buf, geom_bytes, binning_buf, binning_bytes, image_buf,
+                                   image_bytes, 0, stream);
+    }
+    if (!out->radii || !geom_buf) return fail(GOI_ERR_INVALID_ARG, "radii/geom_buf are NULL");
+    if (geom_bytes < goi_geom_bytes(g->P, g->S)) return fail(GOI_ERR_WORKSPACE, "geometry buffer too small");
+    if (binning_bytes < goi_binning_bytes(capacity)) return fail(GOI_ERR_WORKSPACE, "binning buffer too small for the capacity");
+    cudaStream_t st = (cudaStream_t)stream;
+    GeomState gs = carve_geom((char*)geom_buf, g->P, g->S);
+    { StageScope sc(ST_PREPROCESS, st); GOI_CUDA(launch_preprocess_fwd(*view, *g, out->radii, gs, st), "preprocess"); }
+    { StageScope sc(ST_SCAN, st); GOI_CUDA(run_scan(gs, g->P, st), "prefix sum"); }
+    rc = forward_render_impl(view, g, out, nullptr, geom_buf, geom_bytes, binning_buf, binning_bytes, image_buf,
+                             image_bytes, capacity, stream, /*device_count=*/true);
+    if (rc != GOI_OK) return rc;
+    GOI_CUDA(cudaMemcpyAsync(status_host, gs.meta, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "status copy");
+    return GOI_OK;
 }
 
 int goi_forward(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,

@@ -99,16 +99,16 @@ __global__ void __launch_bounds__(256) k_emit_keys(int P, const uint32_t* __rest
                                                    const float4* __restrict__ geo,
                                                    const uint32_t* __restrict__ offsets,
                                                    const uint2* __restrict__ rect, int gx, int W, int H,
-                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t cap)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t off = 0, end = 0, idx = 0;
     uint32_t minx = 0, miny = 0, maxx = 0, maxy = 0;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-    if (k < P) {
-        off = (k == 0) ? 0 : offsets[k - 1];
-        end = offsets[k];
+    if (k < P) {                              // (cap: the caller's blob holds only that many instances; an
+        off = min((k == 0) ? 0u : offsets[k - 1], cap);   //  overflowing view is flagged and re-rendered, never overrun)
+        end = min(offsets[k], cap);
     }
     const bool active = off != end;           // otherwise culled, or no tile survives the exact test
     if (active) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_emit_keys(int P, const uint32_t* __rest
 // once (coalesced) plus one halo key; position i is a run boundary iff key[i-1] != key[i], and a boundary closes the
 // left tile's run and opens the right one's.
 __global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint32_t* __restrict__ keys,
-                                                     uint2* __restrict__ ranges)
+                                                     uint2* __restrict__ ranges, uint32_t T)
 {
     __shared__ uint32_t s_key[257];
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -168,11 +168,22 @@ __global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint32_t* 
     __syncthreads();
     if (i >= L) return;
     const uint32_t left = s_key[threadIdx.x], here = s_key[threadIdx.x + 1];
+    // (keys >= T are the padding of goi_forward_async: they sort behind every tile and open no range)
     if (left != here) {
-        ranges[here].x = (uint32_t)i;
-        if (i > 0) ranges[left].y = (uint32_t)i;
+        if (here < T) ranges[here].x = (uint32_t)i;
+        if (i > 0 && left < T) ranges[left].y = (uint32_t)i;
     }
-    if (i == L - 1) ranges[here].y = (uint32_t)L;
+    if (i == L - 1 && here < T) ranges[here].y = (uint32_t)L;
+}
+
+// goi_forward_async: the instance count R is only known on the device.  Flags R > capacity and fills the unused tail
+// [min(R, capacity), capacity) of the key array with a key that sorts behind every tile id.
+__global__ void __launch_bounds__(256) k_pad_keys(Meta* __restrict__ meta, uint32_t cap, uint32_t* __restrict__ keys)
+{
+    const uint32_t R = meta->num_rendered;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { meta->overflow = R > cap ? 1u : 0u; meta->capacity = cap; }
+    for (uint64_t i = (uint64_t)min(R, cap) + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = 0xffffffffu;
 }
 
 // Longest-list-first block order for the composites (one CTA, T tiles): the hardware hands out blocks in index order,
@@ -253,7 +264,7 @@ static int tile_id_bits(uint32_t tiles)
 
 cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const GeomState& gs,
                         const BinningState& bs, const ImageState& is, int64_t R, int* selector_out,
-                        cudaStream_t st)
+                        cudaStream_t st, bool device_count)
 {
     (void)radii;
     const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
@@ -266,14 +277,20 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     }
 
     stage_begin(ST_EMIT, st);
+    if (device_count) {
+        k_pad_keys<<<148 * 2, 256, 0, st>>>(gs.meta, (uint32_t)R, bs.keys[0]);
+        count_launches(1);
+    }
     k_emit_keys<<<(P + 255) / 256, 256, 0, st>>>(P, gs.order[0], gs.geo, gs.point_offsets, gs.rect, gx, v.width,
-                                                 v.height, bs.keys[0], bs.vals[0]);
+                                                 v.height, bs.keys[0], bs.vals[0],
+                                                 device_count ? (uint32_t)R : 0xffffffffu);
     stage_end(ST_EMIT, st);
     count_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
-    const int end_bit = tile_id_bits((uint32_t)(gx * gy));
+    // (the padding key's low bits are all ones: one more id than the tiles need keeps it behind every tile)
+    const int end_bit = tile_id_bits((uint32_t)(gx * gy) + (device_count ? 1u : 0u));
     cub::DoubleBuffer<uint32_t> dk(bs.keys[0], bs.keys[1]);
     cub::DoubleBuffer<uint32_t> dv(bs.vals[0], bs.vals[1]);
     size_t need = 0;
@@ -288,7 +305,7 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
     if (e != cudaSuccess) return e;
 
     stage_begin(ST_RANGES, st);
-    k_tile_ranges<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, dk.Current(), is.ranges);
+    k_tile_ranges<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, dk.Current(), is.ranges, (uint32_t)(gx * gy));
     e = launch_tile_order(gx * gy, is.ranges, is.tile_order, st);
     stage_end(ST_RANGES, st);
     count_launches(1);

@@ -15,8 +15,10 @@ constexpr int COMPOSITE_THREADS = 256;    // one thread per pixel of a tile, 8 w
 // Device-side counters written by the kernels and read back by the host where needed.
 struct Meta {
     uint32_t num_rendered;       // R, from the prefix sum
+    uint32_t overflow;           // goi_forward_async: R exceeded the capacity of the caller's binning blob
     uint32_t prefilter_violation;
-    uint32_t reserved[62];
+    uint32_t capacity;           // goi_forward_async: that capacity
+    uint32_t reserved[60];       // [2..3]: goi_read_stats counter
 };
 
 // Geometry scratch ("geomBuffer"): per-Gaussian records produced by preprocess and
@@ -101,9 +103,11 @@ struct StageScope {
 cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int32_t* radii,
                                   const GeomState& gs, cudaStream_t st);
 cudaError_t run_scan(const GeomState& gs, int P, cudaStream_t st);
+// R = the instance count when the host knows it (device_count = false), else the CAPACITY of the binning blob: the
+// true count is then read from gs.meta on the device, emission is bounded and the key tail padded (goi_forward_async)
 cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const GeomState& gs,
                         const BinningState& bs, const ImageState& is, int64_t R, int* selector_out,
-                        cudaStream_t st);
+                        cudaStream_t st, bool device_count = false);
 size_t scan_temp_bytes_for(int P);
 size_t sort_temp_bytes_for(int64_t R);
 

@@ -25,7 +25,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GOI_RASTER_LIB", os.path.join(_HERE, "..", "lib", "libgoi_raster.so"))
-GOI_ABI_VERSION = 4
+GOI_ABI_VERSION = 5
 GOI_MAX_SEM = 64
 GOI_MASK_APE, GOI_MASK_OSH = 0, 1
 GOI_RAW_OPACITY, GOI_RAW_SCALE, GOI_RAW_ROTATION = 1, 2, 4
@@ -94,6 +94,9 @@ SYMBOLS = {
     "goi_forward_auto": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                    C.c_void_p, C.POINTER(C.c_int64)]),
+    "goi_forward_async": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_size_t,
+                                    C.c_void_p, C.c_void_p]),
     "goi_forward": (C.c_int, [C.POINTER(goi_view), C.POINTER(goi_gaussians), C.POINTER(goi_fwd_out),
                               ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p,
                               C.POINTER(C.c_int64)]),
@@ -127,14 +130,25 @@ GOI_NUM_STAGES = 9
 import threading
 
 
+class BinningOverflow(RuntimeError):
+    """An asynchronously rendered view had more instances than its binning blob could hold: its outputs (and the
+    gradients back-propagated from them) are undefined.  Render the view / redo the step; the capacity estimate has
+    already been raised."""
+
+
 class _DeviceState:
-    __slots__ = ("grad_arena", "grad_accumulate", "r_guess", "last_num_rendered")
+    __slots__ = ("grad_arena", "grad_accumulate", "r_guess", "last_num_rendered", "async_binning", "pending",
+                 "status_pool", "headroom")
 
     def __init__(self):
         self.grad_arena = None
         self.grad_accumulate = False
         self.r_guess = 0                 # running upper estimate of the instance count (sizes the binning blob)
         self.last_num_rendered = 0       # R of the most recent forward on this device
+        self.async_binning = False       # goi_forward_async: no num_rendered read-back per view
+        self.pending = []                # [(status tensor (pinned), cuda event, capacity)] not yet examined
+        self.status_pool = []            # recycled pinned status words
+        self.headroom = 1.10             # capacity = headroom x the running estimate
 
 
 _state_lock = threading.Lock()
@@ -166,6 +180,44 @@ def set_grad_arena(arena, accumulate=False, device=None):
     with _state_lock:
         st.grad_arena = arena
         st.grad_accumulate = bool(accumulate) and arena is not None
+
+
+def set_async_binning(on: bool, device=None, headroom: float = 1.10):
+    """Training-loop mode (no host sync on the fast path): forwards on `device` run through
+    goi_forward_async -- the binning blob is sized for `headroom` x the running instance-count estimate and the count
+    stays on the device, so the host never waits for the GPU inside a view and runs ahead of it.  Each view leaves a
+    4-word status in pinned host memory; `check_async()` examines the ones that have landed and raises BinningOverflow
+    if a view did not fit (call it at least once per optimisation step, with wait=True before trusting a step's
+    result).  The first view on a device always takes the synchronous path to seed the estimate."""
+    st = device_state(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    st.async_binning = bool(on)
+    st.headroom = float(headroom)
+
+
+def check_async(device=None, wait: bool = False) -> int:
+    """Examine the status words of asynchronously rendered views on `device`.  wait=False: only those whose copy has
+    completed; wait=True: all of them (blocks).  Returns how many views were examined; raises BinningOverflow."""
+    st = device_state(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    n, worst = 0, None
+    while st.pending:
+        status, ev, cap = st.pending[0]
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            break
+        st.pending.pop(0)
+        R, overflow, violation = int(status[0]), int(status[1]), int(status[2])
+        st.status_pool.append(status)
+        st.last_num_rendered = R
+        st.r_guess = max(R, int(0.9 * st.r_guess))
+        n += 1
+        if violation:
+            raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
+        if overflow:
+            worst = (R, cap) if worst is None or R > worst[0] else worst
+    if worst is not None:
+        raise BinningOverflow(f"a view produced {worst[0]} tile instances but its binning blob was sized for {worst[1]}")
+    return n
 
 
 def num_rendered(device=None) -> int:
@@ -300,6 +352,26 @@ def rasterize_gaussians(bg, means3D, colors, semantics, opacity, scales, rotatio
         # headroom), so prepare + render run inside one C call and the device is refilled right after the
         # one host sync of the path; a wrong guess costs one re-allocation.
         st = device_state(dev)
+        if st.async_binning and st.r_guess > 0 and P and not debug:
+            # no host sync: the instance count stays on the device; the blobs are carved for `cap` instances
+            cap = int(st.r_guess * st.headroom) + 4096
+            bin_bytes = L.goi_binning_bytes(cap)
+            binning = torch.empty((bin_bytes,), **u8)
+            if not st.status_pool:                  # recycle landed status words; allocate pinned memory only in bulk
+                check_async(dev, wait=False)
+                if not st.status_pool:
+                    if len(st.pending) >= 256:
+                        check_async(dev, wait=True)
+                    else:
+                        st.status_pool = list(torch.zeros((64, 4), dtype=torch.int32).pin_memory().unbind(0))
+            status = st.status_pool.pop()
+            _check(L.goi_forward_async(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,
+                                       binning.data_ptr(), bin_bytes, cap, img.data_ptr(), img_bytes, stream,
+                                       status.data_ptr()), "goi_forward_async")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            st.pending.append((status, ev, cap))
+            return cap, out_color, out_sem, out_depth, out_alpha, radii, geom, binning, img
         bin_bytes = L.goi_binning_bytes(max(int(st.r_guess * 1.25), 4 * P, 1 << 16)) if P else L.goi_binning_bytes(0)
         binning = torch.empty((bin_bytes,), **u8)
         rc = L.goi_forward_auto(C.byref(view), C.byref(g), C.byref(out), geom.data_ptr(), geom_bytes,

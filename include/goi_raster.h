@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GOI_ABI_VERSION 4
+#define GOI_ABI_VERSION 5
 #define GOI_MAX_SEM 64          /* largest supported semantic channel count */
 #define GOI_TILE 16             /* tile edge in pixels (config.h:16-17 BLOCK_X/Y) */
 
@@ -200,6 +200,21 @@ int goi_forward_render(const goi_view* view, const goi_gaussians* g,
 int goi_forward_auto(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
                      void* geom_buf, size_t geom_bytes, void* binning_buf, size_t binning_bytes,
                      void* image_buf, size_t image_bytes, void* stream, int64_t* num_rendered);
+
+/* ---- forward WITHOUT any host synchronisation (training loops; SURVEY.md section 8b "no host sync on the fast
+ * path").  The reference blocks the host once per view to read num_rendered (rasterizer_impl.cu:285) because its
+ * binning buffer is sized from it; here the caller sizes the binning blob for a CAPACITY of instances
+ * (goi_binning_bytes(capacity), e.g. 1.1 x the count of recent views) and the count stays on the device: key emission
+ * is bounded by the capacity, the unused tail of the key array is padded with a key that sorts last, and the sort,
+ * the range scan and both composites run over `capacity` entries' worth of storage.
+ * status_host: 4 x uint32 in HOST memory (pinned, so the copy is asynchronous).  The library enqueues a copy of
+ *   { num_rendered, overflow (num_rendered > capacity), prefilter_violation, capacity }
+ * behind the view's kernels.  The caller MUST look at it (after an event / stream sync of its choosing, e.g. once per
+ * optimisation step) before it trusts the view: with overflow != 0 the outputs are undefined and the view has to be
+ * rendered again with capacity >= num_rendered.  The blobs go to goi_backward with num_rendered = capacity. */
+int goi_forward_async(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
+                      void* geom_buf, size_t geom_bytes, void* binning_buf, size_t binning_bytes, int64_t capacity,
+                      void* image_buf, size_t image_bytes, void* stream, uint32_t* status_host);
 
 /* ---- forward, callback form: signature-for-signature stand-in for
  * Rasterizer::forward (rasterizer.h:34-62).  Returns num_rendered through

@@ -419,6 +419,44 @@ def test_callback_and_two_phase_forward_equal_forward_auto():
     assert rc == -3 and b"binning" in L.goi_last_error()
 
 
+def test_async_forward_equals_synchronous_and_flags_overflow():
+    """goi_forward_async (no num_rendered read-back: capacity-sized binning, padded key tail) must give bit-identical
+    images and gradients to the synchronous path, and a view that does not fit its capacity must be flagged."""
+    from diff_gaussian_rasterization import _C
+    P, W, H, S = 40_000, 400, 267, 16
+    g, cam, bg = make_scene(P, W, H, S, 71)
+    w = make_loss_weights(S, W, H, 71)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    _C.device_state(dev).r_guess = 0                      # (the estimate decays slowly: forget earlier tests' scenes)
+    base = run_cuda(g, cam, bg, w)                        # synchronous; seeds the instance-count estimate
+    R = _C.num_rendered()
+    try:
+        _C.set_async_binning(True, dev, headroom=1.07)
+        a = run_cuda(g, cam, bg, w)
+        assert _C.check_async(dev, wait=True) == 1 and _C.num_rendered() == R
+        for k in ("color", "semantics", "depth", "alpha", "radii"):
+            assert torch.equal(a[k], base[k]), k
+        for k, v in base["grads"].items():
+            if v is not None:
+                scale = float(v.abs().max()) or 1.0
+                assert float((a["grads"][k] - v).abs().max()) <= 2e-6 * scale, k     # (atomics: order-dependent rounding)
+        # a second scene with 3x the instances against the stale estimate: must be flagged, not silently truncated
+        g2, cam2, bg2 = make_scene(3 * P, W, H, S, 72)
+        run_cuda(g2, cam2, bg2)
+        with pytest.raises(_C.BinningOverflow):
+            _C.check_async(dev, wait=True)
+        # the estimate has been raised: the same view now fits and equals the synchronous render
+        b = run_cuda(g2, cam2, bg2)
+        assert _C.check_async(dev, wait=True) == 1
+        _C.set_async_binning(False, dev)
+        c = run_cuda(g2, cam2, bg2)
+        for k in ("color", "semantics", "depth", "alpha", "radii"):
+            assert torch.equal(b[k], c[k]), k
+    finally:
+        _C.set_async_binning(False, dev)
+        _C.device_state(dev).pending.clear()
+
+
 # ---------------------------------------------------------------------------------------------
 # (c) size-independent properties at the full BASELINE config-2 size (1M Gaussians, 1600x1000, S=16)
 # ---------------------------------------------------------------------------------------------
