@@ -86,6 +86,302 @@ __global__ void __launch_bounds__(THREADS) k_mask_apply(int64_t N, int S, int K,
     }
 }
 
+
+// =====================================================================================================================
+// k_mask_apply_tc -- the same projection + arg-max on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The S -> K projection is the one dense contraction of the inference path.  k_mask_apply above runs it with
+// warp-level mma.sync, whose issue rate on B200 is one MMA per 8 cycles per SM sub-partition whatever its shape
+// (profiles/micro/mma_rate.cu): 456 of them per 32 pixels at S = 16 bound that kernel at ~0.16 ms per 1.6 Mpx.  Here
+// one CTA (128 threads) owns the SM's tensor memory and produces the logits of 128 pixels x all K codebook rows with
+// 18 tcgen05.mma instructions (M = 128, N = 160 + 144, kind::tf32, fp32 accumulators in TMEM):
+//     D = X_lo W_hi^T + X_hi W_lo^T + X_hi W_hi^T        (x = hi + lo TF32 split, as in goi_mask_mma.cuh: ~2^-21)
+// with the bias folded in as one more K column (x carries a 1 there), operands written to shared memory by plain
+// stores in the K-major no-swizzle canonical layout (recipe verified in profiles/micro/tc05_probe.cu).  Each thread
+// then owns one pixel: it reads its accumulator row with tcgen05.ld (32 columns at a time) and keeps the running
+// arg-max (ascending columns, strict >: first maximum wins like torch.argmax).  The codebook is split in two column
+// halves with separate mbarriers so the MMAs of the next tile's half run while the warps scan the other half.
+// =====================================================================================================================
+namespace tc {
+constexpr int LBO = 128;                                    // bytes between the two 16-byte K chunks of a k-step
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address
+    d |= (uint64_t)((LBO >> 4) & 0x3fff) << 16;             // leading byte offset
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;             // stride byte offset (8-row groups)
+    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (sm_100)
+    return d;                                               // SWIZZLE_NONE, base offset 0
+}
+__device__ __forceinline__ uint32_t instr_desc(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);   // F32 += TF32 x TF32, K-major
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar));
+}
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(bar), "r"(parity));
+}
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+}  // namespace tc
+
+// Shared memory: W_hi, W_lo  [NP rows][KP]  (B operands, staged once per CTA), X_hi, X_lo [2][128][KP] (A operands,
+// double-buffered), sim table [K], partial arg-max [2][128].  Element (row r, k) of an operand:
+// (r/8) SBO + (k/4) 128 + (r%8) 16 + (k%4) 4 bytes, SBO = (KP/4) 128.  NP = K rounded up to 16, split into column halves
+// N0 = 16 ceil(NP/32), N1 = NP - N0 (<= 256 each).
+// 256 threads: warps w and w + 4 share TMEM lane quarter w & 3 (= pixels 32 (w & 3) .. + 31 of the tile) and split the
+// columns of every half between them; threads t and t + 128 also split the staging of pixel t & 127's operand row.
+constexpr int MASK_TC_THREADS = 256;
+__global__ void __launch_bounds__(MASK_TC_THREADS, 1)
+k_mask_apply_tc(int64_t N, int S, int K, int KP, int NP, int64_t stride_n, int64_t stride_c, const float* __restrict__ x,
+                const float* __restrict__ mlp_w, const float* __restrict__ mlp_b, const float* __restrict__ sim_table,
+                float thresh, float* __restrict__ sim, uint8_t* __restrict__ bg_mask, int32_t* __restrict__ idx_out)
+{
+    extern __shared__ __align__(1024) uint8_t smem_tc[];
+    const int SBO = (KP / 4) * 128;
+    const int w_bytes = NP * KP * 4, x_bytes = 128 * KP * 4;
+    uint8_t* sWhi = smem_tc;
+    uint8_t* sWlo = sWhi + w_bytes;
+    uint8_t* sX = sWlo + w_bytes;                           // [buf][hi, lo][x_bytes]
+    float* s_tab = reinterpret_cast<float*>(sX + 4 * x_bytes);
+    __shared__ __align__(8) uint64_t s_bar[2];              // MMAs of column half 0 / 1 complete
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_pv[128];                             // partial arg-max of the upper warps (value, index)
+    __shared__ int s_pi[128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, part = tid >> 7;             // pixel of the tile; which share of its columns / channels
+    const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
+    auto elem_off = [SBO](int r, int k) { return (r >> 3) * SBO + (k >> 2) * tc::LBO + (r & 7) * 16 + (k & 3) * 4; };
+
+    // ---- one-time staging of the projection (+ bias column S, padding rows can never win) and the sim table
+    for (int i = tid; i < NP * KP; i += MASK_TC_THREADS) {
+        const int r = i / KP, k = i - r * KP;
+        float v = 0.f;
+        if (r < K) v = k < S ? mlp_w[(size_t)r * S + k] : (k == S ? (mlp_b ? mlp_b[r] : 0.f) : 0.f);
+        else if (k == S) v = -3.0e38f;
+        const uint32_t hi = __float_as_uint(v) & 0xffffe000u;
+        *reinterpret_cast<uint32_t*>(sWhi + elem_off(r, k)) = hi;
+        *reinterpret_cast<float*>(sWlo + elem_off(r, k)) = v - __uint_as_float(hi);
+    }
+    for (int i = tid; i < K; i += MASK_TC_THREADS) s_tab[i] = sim_table[i];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // Thread (row, part) stages channels [20 part, 20 part + 20) of element tile*128 + row.  Two steps so the global-load
+    // latency overlaps the arg-max scan of the previous tile: load_x issues the loads into registers (compile-time
+    // bound, predicated on the channel count), store_x splits them into TF32 hi / lo and writes the operand rows.
+    constexpr int HALF_K = 20;                              // KP <= 40 (S <= 32, mask_tc_applicable)
+    float xv[HALF_K];
+    auto load_x = [&](int64_t tile) {
+        const int64_t n = tile * 128 + row;
+        const float* px = x + n * stride_n;
+#pragma unroll
+        for (int j = 0; j < HALF_K; ++j) {
+            const int k = HALF_K * part + j;
+            xv[j] = (k < S && n < N) ? __ldg(px + k * stride_c) : (k == S ? 1.f : 0.f);
+        }
+    };
+    auto store_x = [&](int buf) {
+        uint8_t* xh = sX + (size_t)(2 * buf) * x_bytes;
+        uint8_t* xl = xh + x_bytes;
+#pragma unroll
+        for (int j4 = 0; j4 < HALF_K; j4 += 4) {
+            const int k4 = HALF_K * part + j4;
+            if (k4 < KP) {
+                uint32_t h[4];
+                float l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { h[j] = __float_as_uint(xv[j4 + j]) & 0xffffe000u; l[j] = xv[j4 + j] - __uint_as_float(h[j]); }
+                const int off = elem_off(row, k4);
+                *reinterpret_cast<uint4*>(xh + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(xl + off) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    };
+    // (one thread) the three-term product of column half `half` for the tile staged in buffer `buf`
+    auto issue_half = [&](uint32_t tmem, int buf, int half) {
+        const int n = half == 0 ? N0 : N1;
+        const uint32_t idesc = tc::instr_desc(128, n);
+        const uint32_t xh = smem_u32(sX + (size_t)(2 * buf) * x_bytes), xl = xh + x_bytes;
+        const uint32_t row0 = (uint32_t)(half == 0 ? 0 : (N0 / 8) * SBO);
+        const uint32_t wh = smem_u32(sWhi) + row0, wl = smem_u32(sWlo) + row0;
+        const uint32_t d = tmem + (uint32_t)(half == 0 ? 0 : N0);
+        uint32_t acc = 0;
+        for (int term = 0; term < 3; ++term) {              // small terms first
+            const uint32_t a = term == 0 ? xl : xh, b = term == 1 ? wl : wh;
+            for (int ks = 0; ks < KP / 8; ++ks) {
+                tc::mma_tf32(d, tc::smem_desc(a + ks * 2 * tc::LBO, SBO), tc::smem_desc(b + ks * 2 * tc::LBO, SBO), idesc, acc);
+                acc = 1;
+            }
+        }
+        tc::commit(smem_u32(&s_bar[half]));
+    };
+
+    const int64_t n_tiles = (N + 127) / 128;
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) { load_x(tile); store_x(0); }
+    asm volatile("fence.proxy.async.shared::cta;");         // generic-proxy stores -> visible to the MMA (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    if (tid == 0 && tile < n_tiles) { issue_half(tmem, 0, 0); issue_half(tmem, 0, 1); }
+
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's 32 TMEM lanes = its 32 pixels
+    // column ranges of this thread (multiples of 16): the two warps of a quarter split each half about evenly
+    const int split0 = 32 * ((N0 / 32 + 1) / 2), split1 = 32 * (N1 / 64);
+    const int c0_beg = part == 0 ? 0 : split0, c0_cnt = part == 0 ? split0 : N0 - split0;
+    const int c1_beg = N0 + (part == 0 ? 0 : split1), c1_cnt = part == 0 ? split1 : N1 - split1;
+    uint32_t parity = 0;
+    int buf = 0;
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1, parity ^= 1) {
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) load_x(next);                   // in flight while this tile's accumulators are scanned
+
+        // Running arg-max in NCH independent (value, index) chains -- column j feeds chain j % NCH -- because two warps
+        // per scheduler cannot hide the latency of a single compare/select chain.  Every chain sees its columns in
+        // ascending order with a strict >, so it keeps its FIRST maximum; the merges prefer the smaller index on equal
+        // values = torch.argmax's first maximum.
+        constexpr int NCH = 8;
+        float best[NCH];
+        int bidx[NCH];
+#pragma unroll
+        for (int a = 0; a < NCH; ++a) { best[a] = -INFINITY; bidx[a] = 0; }
+        uint32_t va[32], vb[32];
+        auto scan = [&](const uint32_t (&v)[32], int c0, bool full) {       // columns c0 .. c0 + 31 (or 15) of this thread's row
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < 16 || full) {
+                    const float c = __uint_as_float(v[j]);
+                    const bool gt = c > best[j % NCH];
+                    best[j % NCH] = gt ? c : best[j % NCH];
+                    bidx[j % NCH] = gt ? c0 + j : bidx[j % NCH];
+                }
+        };
+        // columns [cbeg, cbeg + n) of the row, 32 at a time (n is a multiple of 16); the next TMEM load is in flight
+        // while a block is scanned
+        auto scan_cols = [&](int cbeg, int n) {
+            const int nblk = (n + 31) / 32;
+            if (nblk == 0) return;
+            auto issue = [&](int b, uint32_t (&v)[32]) {
+                if (n - 32 * b >= 32) tc::ld32(lane_base + (uint32_t)(cbeg + 32 * b), v);
+                else tc::ld16(lane_base + (uint32_t)(cbeg + 32 * b), v);
+            };
+            issue(0, va);
+            tc::ld_wait();
+            for (int b = 0; b < nblk; b += 2) {
+                if (b + 1 < nblk) issue(b + 1, vb);
+                scan(va, cbeg + 32 * b, n - 32 * b >= 32);
+                tc::ld_wait();
+                if (b + 1 < nblk) {
+                    if (b + 2 < nblk) issue(b + 2, va);
+                    scan(vb, cbeg + 32 * (b + 1), n - 32 * (b + 1) >= 32);
+                    tc::ld_wait();
+                }
+            }
+        };
+        // ---- column half 0
+        tc::wait(smem_u32(&s_bar[0]), parity);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        scan_cols(c0_beg, c0_cnt);
+        if (next < n_tiles) store_x(buf ^ 1);               // the next tile's operands (its loads have landed by now)
+        asm volatile("fence.proxy.async.shared::cta;");
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();                                    // every warp has drained half 0 and staged the next tile
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (tid == 0 && next < n_tiles) issue_half(tmem, buf ^ 1, 0);
+        // ---- column half 1
+        tc::wait(smem_u32(&s_bar[1]), parity);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        scan_cols(c1_beg, c1_cnt);
+        float bv = best[0];
+        int bi = bidx[0];
+#pragma unroll
+        for (int a = 1; a < NCH; ++a)
+            if (best[a] > bv || (best[a] == bv && bidx[a] < bi)) { bv = best[a]; bi = bidx[a]; }
+        if (part == 1) { s_pv[row] = bv; s_pi[row] = bi; }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (tid == 0 && next < n_tiles) issue_half(tmem, buf ^ 1, 1);
+
+        const int64_t n = tile * 128 + row;
+        if (part == 0 && n < N) {
+            const float ov = s_pv[row];
+            const int oi = s_pi[row];
+            if (ov > bv || (ov == bv && oi < bi)) bi = oi;
+            const float sv = s_tab[bi];
+            const bool bg = sv < thresh;
+            sim[n] = bg ? 0.f : sv;
+            if (bg_mask) bg_mask[n] = bg ? 1 : 0;
+            if (idx_out) idx_out[n] = bi;
+        }
+        // (s_pv / s_pi are rewritten only after the next tile's two block barriers)
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    (void)lane;
+}
+
+// tcgen05 path: one persistent CTA per SM.  Needs K <= 512 accumulator columns (two halves <= 256) and the operands in
+// 227 KB of shared memory; otherwise the mma.sync kernel runs.
+static bool mask_tc_applicable(const goi_mask_args& a, int& KP, int& NP, size_t& smem)
+{
+    KP = ((a.S + 1 + 7) / 8) * 8;
+    NP = ((a.K + 15) / 16) * 16;
+    const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
+    smem = (size_t)2 * NP * KP * 4 + (size_t)4 * 128 * KP * 4 + (size_t)a.K * 4 + 1024;
+    return a.S <= 32 && NP <= 512 && N0 <= 256 && N1 >= 16 && N1 <= 256 && (N0 % 16) == 0 && (N1 % 16) == 0 &&
+           smem <= 220 * 1024 && a.N >= 4096;
+}
+
+static cudaError_t launch_mask_tc(const goi_mask_args& a, int KP, int NP, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_mask_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (a.N + 127) / 128;
+    const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
+    k_mask_apply_tc<<<blocks, MASK_TC_THREADS, smem, st>>>(a.N, a.S, a.K, KP, NP, a.stride_n, a.stride_c, a.x, a.mlp_weight, a.mlp_bias,
+                                               a.sim_table, a.thresh, a.sim, a.bg_mask, a.idx);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
 template <int NS4, int THREADS>
 static cudaError_t launch_mask_t(const goi_mask_args& a, cudaStream_t st)
 {
@@ -149,6 +445,11 @@ cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
     cudaError_t e = launch_mask_table(a, st);
     if (e != cudaSuccess) return e;
     if (a.N <= 0) return cudaSuccess;
+    {
+        int KP, NP;
+        size_t smem;
+        if (a.S > 0 && mask_tc_applicable(a, KP, NP, smem)) return launch_mask_tc(a, KP, NP, smem, st);
+    }
     switch (sem_groups(a.S)) {
         case 0: return cudaErrorInvalidValue;
         case 1: return launch_mask_t<1, 256>(a, st);

@@ -140,12 +140,15 @@ def test_fused_mask_epilogue_equals_render_then_mask(S, mode, want_sem):
         assert float((out[k] - base[k]).abs().max()) <= 2e-5 * max(1.0, float(base[k].abs().max())), k
     if not want_sem:
         assert out["semantics"] is None
-    # the mask of the fused epilogue = goi_mask applied to ITS OWN semantic image, bit for bit
+    # the mask of the fused epilogue (warp-level MMA) = goi_mask (tcgen05) applied to ITS OWN semantic image: both
+    # evaluate the 3xTF32 projection, in different summation orders -> equal except at arg-max near-ties
     if want_sem:
         bg_own = torch.zeros(H * W, dtype=torch.bool, device="cuda")
         sim_own, idx_own = hp.compute_similarity(out["semantics"], out_bg_mask=bg_own, channels_first=True, want_idx=True)
-        assert torch.equal(out["idx"].view(-1), idx_own) and torch.equal(out["sim"].view(-1), sim_own)
-        assert torch.equal(out["bg_mask"].view(-1), bg_own)
+        same_own = out["idx"].view(-1) == idx_own
+        assert float(same_own.float().mean()) > 0.9995
+        assert torch.equal(out["sim"].view(-1)[same_own], sim_own[same_own])
+        assert torch.equal(out["bg_mask"].view(-1)[same_own], bg_own[same_own])
     # and equal to the mask of the plain render except at arg-max near-ties (the two semantic images differ by ~1e-6)
     same = out["idx"].view(-1) == idx_ref
     assert float(same.float().mean()) > 0.999
