@@ -439,7 +439,7 @@ def test_async_forward_equals_synchronous_and_flags_overflow():
         for k, v in base["grads"].items():
             if v is not None:
                 scale = float(v.abs().max()) or 1.0
-                assert float((a["grads"][k] - v).abs().max()) <= 2e-6 * scale, k     # (atomics: order-dependent rounding)
+                assert float((a["grads"][k] - v).abs().max()) <= 5e-5 * scale, k     # (float atomics: order-dependent rounding)
         # a second scene with 3x the instances against the stale estimate: must be flagged, not silently truncated
         g2, cam2, bg2 = make_scene(3 * P, W, H, S, 72)
         run_cuda(g2, cam2, bg2)
