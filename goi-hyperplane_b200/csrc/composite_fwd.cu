@@ -491,6 +491,7 @@ k_composite_fwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
             const bool fin = valid && (test_T < 0.0001f);           // pixel saturates: not blended
             const bool hit = valid && !fin;
             done |= fin ? 1 : 0;
+            GOI_STAT_ADD(2, (__any_sync(0xffffffffu, hit) && lane == 0) ? 1u : 0u);
             GOI_STAT_ADD(3, hit ? 1u : 0u);
             const float w = hit ? alpha * T : 0.f;
             T = hit ? test_T : T;
