@@ -178,12 +178,16 @@ __global__ void __launch_bounds__(256) k_tile_ranges(int64_t L, const uint32_t* 
 
 // goi_forward_async: the instance count R is only known on the device.  Flags R > capacity and fills the unused tail
 // [min(R, capacity), capacity) of the key array with a key that sorts behind every tile id.
-__global__ void __launch_bounds__(256) k_pad_keys(Meta* __restrict__ meta, uint32_t cap, uint32_t* __restrict__ keys)
+__global__ void __launch_bounds__(256) k_pad_keys(Meta* __restrict__ meta, uint32_t cap, uint32_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ vals)
 {
     const uint32_t R = meta->num_rendered;
     if (blockIdx.x == 0 && threadIdx.x == 0) { meta->overflow = R > cap ? 1u : 0u; meta->capacity = cap; }
     for (uint64_t i = (uint64_t)min(R, cap) + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+    {
         keys[i] = 0xffffffffu;
+        vals[i] = 0u;                           // (never read back; keeps the sort free of uninitialised loads)
+    }
 }
 
 // Longest-list-first block order for the composites (one CTA, T tiles): the hardware hands out blocks in index order,
@@ -278,7 +282,7 @@ cudaError_t run_binning(const goi_view& v, int P, const int32_t* radii, const Ge
 
     stage_begin(ST_EMIT, st);
     if (device_count) {
-        k_pad_keys<<<148 * 2, 256, 0, st>>>(gs.meta, (uint32_t)R, bs.keys[0]);
+        k_pad_keys<<<148 * 2, 256, 0, st>>>(gs.meta, (uint32_t)R, bs.keys[0], bs.vals[0]);
         count_launches(1);
     }
     k_emit_keys<<<(P + 255) / 256, 256, 0, st>>>(P, gs.order[0], gs.geo, gs.point_offsets, gs.rect, gx, v.width,

@@ -811,7 +811,7 @@ struct BwdWarp {
     static constexpr int NT = NTP + 1;                     // + the moment tile
     static constexpr int ROWF = 8 * NT;                    // floats per scratch row
     static constexpr int CH = 16;                          // walks per chunk
-    static constexpr int PRS = 24;                         // floats per staged payload row (conflict-free LDS.64)
+    static constexpr int PRS = 8 * NKQ;                    // floats per staged payload row: 24 or 40 (= 8 or 24 mod 32: conflict-free LDS.64)
     static constexpr int FG = 80, FT = 20, FRAG_FLOATS = 8 * FG;        // A-fragment order of (w, u), see BwdMma
     static constexpr int NQW = 4 * NKQ;                    // packed lo words of the Q image   (8 NKQ values)
     static constexpr int NRW = 4 * NTP;                    // packed lo words of the R image   (8 NTP values)
@@ -826,7 +826,7 @@ struct BwdWarp {
     static constexpr int OFF_LIDX = OFF_LO + 32 * LOS;                 // [2][CH]
     static constexpr int OFF_RING = OFF_LIDX + 2 * CH;                 // [RING] ids, [RING] list indices
     static constexpr int TOTAL = OFF_RING + 2 * RING;
-    static_assert((NPROD + 1) * 36 <= 2 * FRAG_FLOATS, "G transpose scratch");
+    static_assert((NPROD + 1) * 36 <= 2 * FRAG_FLOATS + 32 * LOS, "G transpose scratch (W, U and the not yet written lo image)");
     static_assert(LOS % 8 == 4, "lo image stride must be conflict-free for LDS.128");
 };
 
@@ -849,7 +849,7 @@ __device__ __forceinline__ uint4 lds128u(uint32_t a)
 __device__ __forceinline__ uint32_t pack_lo(float a, float b) { return (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xffff0000u); }
 
 template <int NS4>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, (NS4 <= 4 ? 16 : 10))
 k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                      const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ cull8, size_t cull_plane,
                      int W, int H, int gx,
@@ -988,7 +988,7 @@ k_composite_bwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
         for (int k = 0; k < C::NQW + C::NRW; ++k) sts_u32(aLo + 4 * k, lo_words[k]);
         // staged payload rows: floats [0, NPROD) are written by cp.async (4 + S of them), [NPROD] = 1 (dL/dalpha
         // column), everything else must read as zero
-        for (int f = 4 + S; f < PRS; ++f) sts32(aPay + 4 * (lane * PRS + f), f == NPROD ? 1.f : 0.f);      // lane = one of the 2 x 16 rows
+        for (int f = 0; f < PRS; ++f) sts32(aPay + 4 * (lane * PRS + f), f == NPROD ? 1.f : 0.f);          // lane = one of the 2 x 16 rows (all finite)
         __syncwarp();
     }
     // Mom[p][m], m = gid: 1, lx, ly, lx^2, lx ly, ly^2 (0 for m = 6, 7) at pixel p = 8 tig + 2 ks + h -> lx = 2 ks + h, ly = tig
@@ -1360,7 +1360,7 @@ cudaError_t launch_composite_bwd(const goi_view& v, const goi_gaussians& g, cons
         case 2: return launch_bwd_warp_t<2>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
         case 3: return launch_bwd_warp_t<3>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
         case 4: return launch_bwd_warp_t<4>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
-        case 8: return launch_bwd_t<8>(v, g, in, out, gs, point_list, cull, is, st);
+        case 8: return launch_bwd_warp_t<8>(v, g, in, gs, point_list, cull8, cull_plane, is, st);
         default: return launch_bwd_t<16>(v, g, in, out, gs, point_list, cull, is, st);
     }
 }

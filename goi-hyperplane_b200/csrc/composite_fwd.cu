@@ -288,7 +288,7 @@ struct FwdWarp {
     static constexpr int NPROD = 4 + 4 * NS4;
     static constexpr int NTC = (NPROD + 7) / 8;            // 8-channel tiles
     static constexpr int CH = 16;                          // walks per chunk = two k-steps
-    static constexpr int PRS = 24;                         // floats per staged payload row (>= 8 NTC; conflict-free B loads)
+    static constexpr int PRS = 8 * (NTC | 1);              // floats per staged payload row: 24 or 40 (= 8 or 24 mod 32: conflict-free B loads)
     static constexpr int RING = 64;                        // queued survivors (<= 16 in process + 47 pending): geometry 32 B + list index
     static constexpr int WBLK = 160;                       // floats per (m-tile, k-step) block of the w operand
     static constexpr int OFF_RGEO = 0;                                 // [RING][8]
@@ -327,7 +327,7 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v)
 }
 
 template <int NS4>
-__global__ void __launch_bounds__(32, 20)
+__global__ void __launch_bounds__(32, (NS4 <= 4 ? 20 : 14))
 k_composite_fwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                      const uint32_t* __restrict__ point_list, int W, int H, int gx,
                      const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
@@ -361,9 +361,9 @@ k_composite_fwd_warp(const uint2* __restrict__ ranges, const uint32_t* __restric
     const float bx0 = (float)wx0, bx1 = (float)min(wx0 + 7, W - 1), by0 = (float)wy0, by1 = (float)min(wy0 + 3, H - 1);
     uint8_t* const my_cull = cull8 + (size_t)warp * cull_plane + range.x;
 
-    // payload rows: floats [4 + S, PRS) are never written by the copies and must read as zero (finite) in the MMA
-    for (int f = 4 + S; f < PRS; ++f) sts32(aPay + 4 * (lane * PRS + f), 0.f);     // lane = one of the 2 x 16 rows
-    if (!sem_vec) for (int f = 0; f < 4 + S; ++f) sts32(aPay + 4 * (lane * PRS + f), 0.f);
+    // Payload rows start as zeros: floats [4 + S, PRS) are never written by the copies, and the rows past the end of a
+    // block's first (partial) chunk enter the MMA with weight 0 -- whatever shared memory held before must not be a NaN.
+    for (int f = 0; f < PRS; ++f) sts32(aPay + 4 * (lane * PRS + f), 0.f);         // lane = one of the 2 x 16 rows
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
@@ -636,6 +636,7 @@ cudaError_t launch_composite_fwd(const goi_view& v, const goi_gaussians& g, cons
             case 2: return launch_fwd_warp_t<2>(v, g, out, gs, point_list, cull8, cull_plane, is, st);
             case 3: return launch_fwd_warp_t<3>(v, g, out, gs, point_list, cull8, cull_plane, is, st);
             case 4: return launch_fwd_warp_t<4>(v, g, out, gs, point_list, cull8, cull_plane, is, st);
+            case 8: return launch_fwd_warp_t<8>(v, g, out, gs, point_list, cull8, cull_plane, is, st);
             default: break;
         }
     }

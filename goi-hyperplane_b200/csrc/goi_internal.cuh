@@ -70,7 +70,7 @@ ImageState   carve_image(char* base, int W, int H);
 BinningState carve_binning(char* base, int64_t R);
 
 inline int sem_groups(int S);
-// floats per scratch row of the tensor-core composite backward: 8 x (payload tiles + 1 moment tile); 0 for S > 16
+// floats per scratch row of the tensor-core composite backward: 8 x (payload tiles + 1 moment tile); 0 for S > 32
 inline int bwd_row_floats(int S);
 inline int sem_groups(int S) {           // float4 groups the composite kernels are instantiated for
     if (S <= 0) return 0;
@@ -83,7 +83,7 @@ inline int sem_groups(int S) {           // float4 groups the composite kernels 
 }
 inline int bwd_row_floats(int S) {
     const int ns4 = sem_groups(S);
-    if (ns4 > 4) return 0;
+    if (ns4 > 8) return 0;                 // S = 64: the direct-atomics kernels
     return 8 * ((4 + 4 * ns4 + 7) / 8 + 1);
 }
 

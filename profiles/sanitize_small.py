@@ -21,7 +21,9 @@ for (P, W, H, S, seed) in ((10_000, 256, 256, 10, 0), (6_000, 250, 197, 16, 2), 
     out2 = common.run_cuda(g, cam, bg, w)
     _C.check_async(dev, wait=True)
     _C.set_async_binning(False, dev)
-    assert torch.equal(out["color"], out2["color"])
+    d = float((out["color"] - out2["color"]).abs().max())
+    print("async vs sync max |d color|", d, "R", _C.num_rendered())
+    assert d == 0.0
     mlp_w, mlp_b, lut, text = make_mask_model(S, seed=seed)
     hp = SemanticHyperplane(mlp_w.cuda(), mlp_b.cuda(), lut.cuda(), text.cuda(), thresh=0.86)
     sim = hp.compute_similarity(out["semantics"].detach(), channels_first=True)
