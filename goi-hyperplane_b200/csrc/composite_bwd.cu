@@ -364,7 +364,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ t
 
 
 // =====================================================================================================================
-// k_composite_bwd_mma -- the same reverse walk with BOTH per-instance pixel reductions on the tensor cores.
+// Tensor-core pixel reductions of the reverse walk (used by k_composite_bwd_warp below).
 //
 // What a (warp, instance) walk has to reduce over the warp's 32 pixels:
 //   payload gradients   dF[ch] = sum_p w(p) g_ch(p)            w = alpha T,  g = the pixel gradients (NPROD values)
@@ -377,7 +377,7 @@ k_composite_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ t
 // and over a chunk of 16 walks two 16-row matrix products: warp-level mma.sync m16n8k8 TF32 with fp32 accumulation
 // and the split  x = hi + lo  (hi = top 19 bits, lo = x - hi exact):  hi.hi + lo.hi + hi.lo reproduces the fp32 product
 // to ~2^-21; Mom holds small integers (exact in TF32), so the moment product needs only u's two halves.
-// A lane publishes just (w, u) per walk -- 2 STS where k_composite_bwd needs 7 + a second transpose -- and the
+// A lane publishes just (w, u) per walk -- 2 STS where k_composite_bwd (S > 32) needs 7 + a second transpose -- and the
 // reduction costs ~11 issue slots per walk instead of ~60.
 //
 // The moments are shifted (exactly: integer offsets) from the block origin to the instance's rounded mean
@@ -422,368 +422,10 @@ __device__ __forceinline__ float lds32(uint32_t a)
     return v;
 }
 
-template <int NS4>
-struct BwdMma {
-    static constexpr int ROW = 1 + NS4;                    // float4 per staged payload row
-    static constexpr int NPROD = 4 + 4 * NS4;              // payload values: r, g, b, depth, semantics
-    static constexpr int NTP = (NPROD + 7) / 8;            // 8-column tiles holding payload gradients
-    static constexpr int NT = NTP + 1;                     // + the moment tile
-    static constexpr int ROWF = 8 * NT;                    // floats per scratch row
-    static constexpr int CH = 16;                          // walks per reduction chunk = M of one MMA
-    static constexpr int RS = 36;                          // floats per row of the one-time G transpose
-    // published (w, u) values live in A-FRAGMENT order: the quad (row g, row g+8) x (pixel 8t+2k, 8t+2k+1) that lane
-    // (gid g, tig t) feeds to k-step k is four consecutive floats at g*FG + t*FT + 4k, so a fragment is ONE LDS.128
-    // landing in four consecutive registers (HMMA operands are register quads)
-    static constexpr int FG = 80, FT = 20;                 // conflict-free LDS.128: FT*t mod 32 distinct, FG = 16 mod 32
-    static constexpr int FRAG_FLOATS = 8 * FG;             // one 16-walk x 32-pixel operand
-    static constexpr int GLS = 8 * NTP + 4;                // per-lane stride of the G-lo image (conflict-free LDS.128)
-    static constexpr int WARP_FLOATS = 2 * FRAG_FLOATS + 32 * GLS;       // (>= NPROD * RS for the G transpose)
-    static size_t smem_bytes(int batch) {
-        return (size_t)2 * batch * (2 + ROW) * sizeof(float4) + (size_t)8 * WARP_FLOATS * sizeof(float);
-    }
-};
-
-template <int NS4, int BATCH>
-__global__ void __launch_bounds__(COMPOSITE_THREADS, 2)
-k_composite_bwd_mma(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
-                    const uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cull, int W, int H, int gx,
-                    const float4* __restrict__ geo, const float4* __restrict__ rgbd, const float* __restrict__ sem,
-                    int S, int sem_vec, const float* __restrict__ bg, const float* __restrict__ out_alpha,
-                    const uint32_t* __restrict__ n_contrib,
-                    const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpixsem,
-                    const float* __restrict__ dL_dpixdepth, const float* __restrict__ dL_dpixalpha,
-                    float* __restrict__ rows)
-{
-    using C = BwdMma<NS4>;
-    constexpr int ROW = C::ROW, NPROD = C::NPROD, NTP = C::NTP, NT = C::NT, ROWF = C::ROWF, CH = C::CH, RS = C::RS,
-                  GLS = C::GLS;
-    constexpr int NSF = NS4 > 0 ? 4 * NS4 : 1;
-    extern __shared__ float4 smem[];
-    float4* s_g0 = smem;                               // [2][BATCH]
-    float4* s_g1 = smem + 2 * BATCH;                   // [2][BATCH]
-    float4* s_pay = smem + 4 * BATCH;                  // [2][BATCH][ROW]
-    float* s_warp = reinterpret_cast<float*>(smem + 4 * BATCH + 2 * BATCH * ROW);   // [8 warps][WARP_FLOATS]
-    __shared__ uint32_t s_max_contrib;
-    __shared__ uint32_t s_cull[2][BATCH];              // the forward's warp-block masks of the staged instances
-    __shared__ uint8_t s_list[8][BATCH];               // per warp: staged indices of the instances it walks
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int gid = lane >> 2, tig = lane & 3;
-    const int tile = (int)tile_order[blockIdx.x];      // longest lists first (k_tile_order)
-    const int tx = tile % gx, ty = tile / gx;
-    const int wx0 = tx * TILE + (warp & 1) * 8, wy0 = ty * TILE + (warp >> 1) * 4;
-    const int px = wx0 + (lane & 7);
-    const int py = wy0 + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    const float wx0f = (float)wx0, wy0f = (float)wy0;
-    const size_t HW = (size_t)H * W;
-    const size_t pix = (size_t)py * W + px;
-    const uint2 range = ranges[tile];
-
-    if (tid == 0) s_max_contrib = 0;
-    if (NS4 > 0 && 4 * NS4 != S)
-        for (int i = tid; i < 2 * BATCH * ROW; i += COMPOSITE_THREADS) s_pay[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // pixel state
-    const uint32_t last_contributor = inside ? n_contrib[pix] : 0;
-    const float T_final = inside ? (1 - out_alpha[pix]) : 0;
-    float T = T_final;
-    float g_rgb[3] = {0.f, 0.f, 0.f}, g_depth = 0.f, g_alpha = 0.f;
-    float g_sem[NSF];
-#pragma unroll
-    for (int i = 0; i < NSF; ++i) g_sem[i] = 0.f;
-    if (inside) {
-        if (dL_dpix) { g_rgb[0] = dL_dpix[pix]; g_rgb[1] = dL_dpix[HW + pix]; g_rgb[2] = dL_dpix[2 * HW + pix]; }
-        if (dL_dpixsem) {
-#pragma unroll
-            for (int ch = 0; ch < 4 * NS4; ++ch)
-                if (ch < S) g_sem[ch] = dL_dpixsem[ch * HW + pix];
-        }
-        if (dL_dpixdepth) g_depth = dL_dpixdepth[pix];
-        if (dL_dpixalpha) g_alpha = dL_dpixalpha[pix];
-    }
-    const float nTf_bg = -T_final * (bg[0] * g_rgb[0] + bg[1] * g_rgb[1] + bg[2] * g_rgb[2]);
-
-    // ---- the warp's constant B operands.  G[p][c] = pixel gradient of payload value c at pixel p (= lane p);
-    //      this lane holds G for pixels 8 tig .. 8 tig + 7 and columns 8 nt + gid: hi halves in registers, lo
-    //      halves in shared memory (re-read once per chunk).  Built by a transpose through the W/U rows.
-    float* my_warp = s_warp + warp * C::WARP_FLOATS;
-    const uint32_t aW = smem_u32(my_warp), aU = aW + C::FRAG_FLOATS * 4, aGlo = aU + C::FRAG_FLOATS * 4 + lane * (GLS * 4);
-    uint32_t bhi[NTP][4][2];
-    __syncthreads();
-    {
-#pragma unroll
-        for (int pv = 0; pv < NPROD; ++pv) {
-            float val;
-            if (pv < 3) val = g_rgb[pv < 3 ? pv : 0];
-            else if (pv == 3) val = g_depth;
-            else val = g_sem[(pv - 4) < NSF && pv >= 4 ? pv - 4 : 0];
-            sts32(aW + (pv * RS + lane) * 4, val);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int nt = 0; nt < NTP; ++nt) {
-            const int c = 8 * nt + gid;
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (c < NPROD) {
-                const float4 v0 = lds128(aW + (c * RS + 8 * tig) * 4), v1 = lds128(aW + (c * RS + 8 * tig + 4) * 4);
-                v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-            }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t hi = tf32_hi(v[2 * ks + h]);
-                    bhi[nt][ks][h] = hi;
-                    sts32(aGlo + ((nt * 4 + ks) * 2 + h) * 4, __uint_as_float(tf32_lo(v[2 * ks + h], hi)));
-                }
-        }
-        __syncwarp();
-    }
-    // Mom[p][m], m = gid: 1, lx, ly, lx^2, lx ly, ly^2 (0 for m = 6, 7) at pixel p = 8 tig + 2 ks + h -> lx = 2 ks + h, ly = tig
-    uint32_t bmom[4][2];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float lx = (float)(2 * ks + h), ly = (float)tig;
-            const float mv = gid == 0 ? 1.f : gid == 1 ? lx : gid == 2 ? ly : gid == 3 ? lx * lx : gid == 4 ? lx * ly :
-                             gid == 5 ? ly * ly : 0.f;
-            bmom[ks][h] = __float_as_uint(mv);
-        }
-    // own-pixel gradients as (x,y) / (z,w) pairs matching the float4 payload rows
-    const float2 g01 = make_float2(g_rgb[0], g_rgb[1]), g2d = make_float2(g_rgb[2], g_depth);
-    float2 gs2[NS4 > 0 ? 2 * NS4 : 1];
-#pragma unroll
-    for (int k = 0; k < 2 * NS4; ++k) gs2[k] = make_float2(g_sem[2 * k], g_sem[2 * k + 1]);
-
-    // the walk only needs list entries [0, max n_contrib over the tile); this warp only those below its own maximum
-    uint32_t warp_max_contrib = last_contributor;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1)
-        warp_max_contrib = max(warp_max_contrib, __shfl_xor_sync(0xffffffffu, warp_max_contrib, off));
-    if (lane == 0 && warp_max_contrib > 0) atomicMax(&s_max_contrib, warp_max_contrib);
-    __syncthreads();
-    const int n = (int)s_max_contrib;                  // entries [0,n) of this tile's list, walked backwards
-    const int nb = (n + BATCH - 1) / BATCH;
-
-    // batch b holds list entries n-1-b*BATCH-j for j = 0..cnt-1 (deepest first)
-    auto stage = [&](int b) {
-        const int buf = b & 1;
-        const int cnt = min(BATCH, n - b * BATCH);
-        constexpr int PARTS = NS4 > 0 ? 2 : 1;
-        for (int wi = tid; wi < cnt * PARTS; wi += COMPOSITE_THREADS) {
-            const int j = wi / PARTS, part = wi % PARTS;
-            const uint32_t li = range.x + (uint32_t)(n - 1 - b * BATCH - j);
-            const uint32_t id = point_list[li];
-            if (part == 0) {
-                cp_async4(&s_cull[buf][j], &cull[li]);
-                cp_async16(&s_g0[buf * BATCH + j], &geo[2 * (size_t)id]);
-                cp_async16(&s_g1[buf * BATCH + j], &geo[2 * (size_t)id + 1]);
-                cp_async16(&s_pay[(buf * BATCH + j) * ROW], &rgbd[id]);
-            } else {
-                float4* dst = &s_pay[(buf * BATCH + j) * ROW + 1];
-                const float* src = sem + (size_t)id * S;
-                if (sem_vec) {
-                    for (int k = 0; k < (S >> 2); ++k) cp_async16(dst + k, src + 4 * k);
-                } else {
-                    for (int c = 0; c < S; ++c) cp_async4(reinterpret_cast<float*>(dst) + c, src + c);
-                }
-            }
-        }
-        cp_async_commit();
-    };
-
-    float last_alpha = 0.f, last_q = 0.f, acc = 0.f;
-    const uint32_t a_g0 = smem_u32(s_g0), a_g1 = smem_u32(s_g1), a_pay = smem_u32(s_pay);
-    const uint32_t a_list = smem_u32(&s_list[warp][0]);
-    const unsigned lt_mask = (1u << lane) - 1u;
-    // this lane's (pixel's) slot in the fragment-ordered operands: walk i adds (i & 7) * FG + (i >> 3) floats
-    const uint32_t pub_off = ((lane >> 3) * C::FT + ((lane & 7) >> 1) * 4 + 2 * (lane & 1)) * 4;
-    const uint32_t pubW = aW + pub_off, pubU = aU + pub_off;
-    const uint32_t fragW = aW + (gid * C::FG + tig * C::FT) * 4, fragU = aU + (gid * C::FG + tig * C::FT) * 4;
-    float* const my_rows = rows + 2 * NT * tig;
-    GOI_STAT_DECL;
-
-    if (nb > 0) stage(0);
-    for (int b = 0; b < nb; ++b) {
-        cp_async_wait_all();
-        __syncthreads();
-        if (b + 1 < nb) stage(b + 1);
-
-        const int buf = b & 1;
-        const int cnt = min(BATCH, n - b * BATCH);
-        const uint32_t ag0 = a_g0 + buf * BATCH * 16, ag1 = a_g1 + buf * BATCH * 16;
-        const uint32_t apay = a_pay + buf * BATCH * ROW * 16;
-        const int first_idx = n - 1 - b * BATCH;        // list index of j = 0
-
-        // ---- this warp's survivors of the batch, in walk order (the forward's cull masks; entries at or behind
-        //      every pixel's last contributor cannot blend here)
-        int nsv = 0;
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
-            const bool keep = (c0 + lane < cnt) && ((s_cull[buf][c0 + lane] >> warp) & 1u) &&
-                              (uint32_t)(first_idx - (c0 + lane)) < warp_max_contrib;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            GOI_STAT_ADD(0, (c0 + lane < cnt) ? 1u : 0u);
-            if (keep) s_list[warp][nsv + __popc(m & lt_mask)] = (uint8_t)(c0 + lane);
-            nsv += __popc(m);
-        }
-        __syncwarp();
-
-        for (int base = 0; base < nsv; base += CH) {
-            const int ccnt = min(CH, nsv - base);
-            uint32_t jreg = 0;
-            if (lane < ccnt) {
-                uint32_t t;
-                asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(t) : "r"(a_list + base + lane) : "memory");
-                jreg = t;
-            }
-            unsigned rowmask = 0;                       // bit i = walk i blended at least one pixel
-
-            // ---------------- walk phase: per-pixel recurrences, publish (w, u) ----------------
-            int j = (int)__shfl_sync(0xffffffffu, jreg, 0);
-            float4 g0 = lds128(ag0 + j * 16), g1 = lds128(ag1 + j * 16);
-            for (int i = 0; i < ccnt; ++i) {
-                GOI_STAT_ADD(1, lane == 0 ? 1u : 0u);
-                const uint32_t list_idx = (uint32_t)(first_idx - j);
-                // payload row: issued now so its latency hides behind the alpha evaluation
-                const uint32_t ap = apay + j * (ROW * 16);
-                const float4 p0 = lds128(ap);
-                float4 s4[NS4 > 0 ? NS4 : 1];
-#pragma unroll
-                for (int k = 0; k < NS4; ++k) s4[k] = lds128(ap + 16 + 16 * k);
-                // next walk's geometry record (software prefetch; the last iteration re-reads its own)
-                const int jn = (int)__shfl_sync(0xffffffffu, jreg, min(i + 1, CH - 1));
-                const float4 g0n = lds128(ag0 + jn * 16), g1n = lds128(ag1 + jn * 16);
-
-                const float dx = g0.x - pxf, dy = g0.y - pyf;
-                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                const float G = expf(power);
-                const float alpha = fminf(0.99f, g1.y * G);
-                // backward.cu:527-529 (behind this pixel's last contributor), :536-542 and power_cut
-                const bool hit = (list_idx < last_contributor) && !(power > 0.0f) && !(power < g1.z) &&
-                                 !(alpha < 1.0f / 255.0f);
-                float w = 0.f, u = 0.f;
-                if (__any_sync(0xffffffffu, hit)) {
-                    GOI_STAT_ADD(2, lane == 0 ? 1u : 0u);
-                    GOI_STAT_ADD(3, hit ? 1u : 0u);
-                    rowmask |= 1u << i;
-                    // branch-free: a rejected lane is a Gaussian of alpha 0 / G 0 (inv = 1, T unchanged, weight 0; the
-                    // (acc, last_q, last_alpha) recurrence stays exact: the next step computes 0 * last_q + 1 * acc)
-                    const float a_eff = hit ? alpha : 0.f;
-                    const float Gh = hit ? G : 0.f;
-                    const float inv = rcp_approx(1.f - a_eff);
-                    T = T * inv;                                // reference: T = T / (1 - alpha)
-                    // q = payload . pixel-gradient + 1 * dL_dalpha: four independent chains in two FFMA2 streams
-                    float2 qa = ffma2(make_float2(p0.x, p0.y), g01, make_float2(g_alpha, 0.f));
-                    float2 qb = fmul2(make_float2(p0.z, p0.w), g2d);
-#pragma unroll
-                    for (int k = 0; k < NS4; ++k) {
-                        qa = ffma2(make_float2(s4[k].x, s4[k].y), gs2[2 * k + 0], qa);
-                        qb = ffma2(make_float2(s4[k].z, s4[k].w), gs2[2 * k + 1], qb);
-                    }
-                    const float q = (qa.x + qa.y) + (qb.x + qb.y);
-                    acc = fmaf(last_alpha, last_q, (1.f - last_alpha) * acc);
-                    last_q = q;
-                    last_alpha = a_eff;
-                    // dL/dalpha = (q - acc) T - T_final bg.g / (1 - alpha)     (backward.cu:592-601)
-                    const float dL_dopa = fmaf(nTf_bg, inv, (q - acc) * T);
-                    w = a_eff * T;
-                    u = (g1.y * dL_dopa) * Gh;                  // dL/dG * G
-                }
-                const uint32_t po = (uint32_t)((i & 7) * (C::FG * 4) + (i >> 3) * 4);
-                sts32(pubW + po, w);
-                sts32(pubU + po, u);
-                g0 = g0n; g1 = g1n; j = jn;
-            }
-            if (rowmask == 0) continue;                 // (warp-uniform) nothing blended in this chunk
-            for (int r = ccnt; r < CH; ++r) {           // rows of a partial chunk must read as zero
-                const uint32_t po = (uint32_t)((r & 7) * (C::FG * 4) + (r >> 3) * 4);
-                sts32(pubW + po, 0.f);
-                sts32(pubU + po, 0.f);
-            }
-            __syncwarp();
-
-            // ---------------- reduction phase: [16 x 32] x [32 x 8 NT] on the tensor cores ----------------
-            float accp[NTP][4], accm[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int nt = 0; nt < NTP; ++nt) { accp[nt][0] = 0.f; accp[nt][1] = 0.f; accp[nt][2] = 0.f; accp[nt][3] = 0.f; }
-            {
-                float glo[8 * NTP];
-#pragma unroll
-                for (int k = 0; k < 2 * NTP; ++k) {
-                    const float4 t = lds128(aGlo + 16 * k);
-                    glo[4 * k] = t.x; glo[4 * k + 1] = t.y; glo[4 * k + 2] = t.z; glo[4 * k + 3] = t.w;
-                }
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const float4 a = lds128(fragW + 16 * ks);           // (a0, a1, a2, a3) of this k-step
-                    const uint32_t h0 = tf32_hi(a.x), h1 = tf32_hi(a.y), h2 = tf32_hi(a.z), h3 = tf32_hi(a.w);
-                    const uint32_t l0 = tf32_lo(a.x, h0), l1 = tf32_lo(a.y, h1), l2 = tf32_lo(a.z, h2), l3 = tf32_lo(a.w, h3);
-#pragma unroll
-                    for (int nt = 0; nt < NTP; ++nt) {
-                        const uint32_t bl0 = __float_as_uint(glo[(nt * 4 + ks) * 2]), bl1 = __float_as_uint(glo[(nt * 4 + ks) * 2 + 1]);
-                        mma_tf32_16x8x8(accp[nt], l0, l1, l2, l3, bhi[nt][ks][0], bhi[nt][ks][1]);      // small terms first
-                        mma_tf32_16x8x8(accp[nt], h0, h1, h2, h3, bl0, bl1);
-                        mma_tf32_16x8x8(accp[nt], h0, h1, h2, h3, bhi[nt][ks][0], bhi[nt][ks][1]);
-                    }
-                }
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const float4 a = lds128(fragU + 16 * ks);
-                    const uint32_t h0 = tf32_hi(a.x), h1 = tf32_hi(a.y), h2 = tf32_hi(a.z), h3 = tf32_hi(a.w);
-                    const uint32_t l0 = tf32_lo(a.x, h0), l1 = tf32_lo(a.y, h1), l2 = tf32_lo(a.z, h2), l3 = tf32_lo(a.w, h3);
-                    mma_tf32_16x8x8(accm, l0, l1, l2, l3, bmom[ks][0], bmom[ks][1]);
-                    mma_tf32_16x8x8(accm, h0, h1, h2, h3, bmom[ks][0], bmom[ks][1]);
-                }
-            }
-            __syncwarp();                               // every lane has read the rows: the next chunk may publish
-
-            // ---------------- epilogue: rows gid (c0, c1) and gid + 8 (c2, c3) of the chunk ----------------
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int r = gid + 8 * half;
-                const int jr = (int)__shfl_sync(0xffffffffu, jreg, r);
-                // moments of the row: (M0, Mx) sit in the group's lane 0, (My, Mxx) in lane 1, (Mxy, Myy) in lane 2
-                const float c0 = accm[2 * half], c1 = accm[2 * half + 1];
-                const float M0 = __shfl_sync(0xffffffffu, c0, lane & ~3);
-                const float Mx = __shfl_sync(0xffffffffu, c1, lane & ~3);
-                const float My = __shfl_sync(0xffffffffu, c0, (lane & ~3) + 1);
-                if ((rowmask >> r) & 1u) {              // else walk r blended nothing (or lies past the chunk): zero row
-                const float2 mean = lds64(ag0 + jr * 16);
-                const uint32_t id = __float_as_uint(lds32(ag1 + jr * 16 + 12));      // preprocess stores the index bits here
-                // shift the moment origin from the block corner to r = rint(mean): l' = l + t, t integer
-                const float tx_ = wx0f - rintf(mean.x), ty_ = wy0f - rintf(mean.y);
-                float m0, m1;
-                if (tig == 0) { m0 = c0; m1 = fmaf(tx_, M0, c1); }
-                else if (tig == 1) { m0 = fmaf(ty_, M0, c0); m1 = fmaf(tx_, fmaf(tx_, M0, 2.f * Mx), c1); }
-                else if (tig == 2) { m0 = fmaf(tx_ * ty_, M0, fmaf(tx_, My, fmaf(ty_, Mx, c0))); m1 = fmaf(ty_, fmaf(ty_, M0, 2.f * My), c1); }
-                else { m0 = 0.f; m1 = 0.f; }
-                float* dst = my_rows + (size_t)id * ROWF;
-                float v[2 * NT];
-#pragma unroll
-                for (int nt = 0; nt < NTP; ++nt) { v[2 * nt] = accp[nt][2 * half]; v[2 * nt + 1] = accp[nt][2 * half + 1]; }
-                v[2 * NTP] = m0; v[2 * NTP + 1] = m1;
-                if constexpr (NT % 2 == 0) {
-#pragma unroll
-                    for (int k = 0; k < NT / 2; ++k) red_add_v4(dst + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NT; ++k) red_add_v2(dst + 2 * k, v[2 * k], v[2 * k + 1]);
-                }
-                }
-            }
-        }
-    }
-    GOI_STAT_FLUSH(4);
-}
-
-
 // =====================================================================================================================
 // k_composite_bwd_warp -- warp-autonomous version: ONE WARP PER CTA, one CTA per 8x4 pixel block (8 per tile).
 //
-// k_composite_bwd_mma above shares its staged batches between the eight warps of a tile and pays for it with a block
+// A CTA-per-tile kernel shares its staged batches between the eight warps of a tile and pays for it with a block
 // barrier per batch: ncu showed 15 % of all warp cycles waiting there, because the SAME blocks of a tile are the
 // heavy ones in every batch.  Here nothing is shared and nothing is synchronised across warps:
 //   * a warp scans the tile's list backwards 32 entries at a time (its bit of the forward's cull masks + the
@@ -796,7 +438,7 @@ k_composite_bwd_mma(const uint2* __restrict__ ranges, const uint32_t* __restrict
 //       W   the per-pixel walk: alpha evaluation of walk i+1 interleaved with the T / acc recurrence of walk i,
 //           branch-free; publishes (w, u) per pixel in A-fragment order;
 //       R   the two pixel reductions [w] x G and [u] x Mom on the tensor cores, moment shift, one vector RED per
-//           lane per row-half into the per-Gaussian scratch row (as k_composite_bwd_mma).
+//           lane per row-half into the per-Gaussian scratch row.
 //   All products: m16n8k8 TF32, x = hi + lo split, three terms, fp32 accumulate (~2^-21 relative).
 // G hi images live in registers; the lo images are bf16-packed in shared memory (2^-19 of G: lo only has to carry
 // the bits hi dropped).  13 KB of shared memory and <= 128 registers per warp: 16 resident warps per SM, each with
@@ -812,7 +454,10 @@ struct BwdWarp {
     static constexpr int ROWF = 8 * NT;                    // floats per scratch row
     static constexpr int CH = 16;                          // walks per chunk
     static constexpr int PRS = 8 * NKQ;                    // floats per staged payload row: 24 or 40 (= 8 or 24 mod 32: conflict-free LDS.64)
-    static constexpr int FG = 80, FT = 20, FRAG_FLOATS = 8 * FG;        // A-fragment order of (w, u), see BwdMma
+    // published (w, u) values live in A-FRAGMENT order: the quad (row g, row g+8) x (pixel 8t+2k, 8t+2k+1) that lane
+    // (gid g, tig t) feeds to k-step k is four consecutive floats at g*FG + t*FT + 4k, so a fragment is ONE LDS.128
+    // landing in four consecutive registers (HMMA operands are register quads); FT*t mod 32 distinct, FG = 16 mod 32
+    static constexpr int FG = 80, FT = 20, FRAG_FLOATS = 8 * FG;
     static constexpr int NQW = 4 * NKQ;                    // packed lo words of the Q image   (8 NKQ values)
     static constexpr int NRW = 4 * NTP;                    // packed lo words of the R image   (8 NTP values)
     static constexpr int LOS = ((NQW + NRW + 7) / 8) * 8 + 4;            // per-lane word stride: 4 x odd = conflict-free LDS.128
@@ -1300,26 +945,6 @@ static cudaError_t launch_bwd_warp_t(const goi_view& v, const goi_gaussians& g, 
         is.ranges, is.tile_order, point_list, cull8, cull_plane, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S,
         sem_vec, v.background, in.out_alpha, is.n_contrib, in.dL_dcolor, in.dL_dsemantic, in.dL_ddepth, in.dL_dalpha,
         gs.grad_rows);
-    count_launches(1);
-    return cudaGetLastError();
-}
-
-template <int NS4>
-static cudaError_t launch_bwd_mma_t(const goi_view& v, const goi_gaussians& g, const goi_bwd_in& in,
-                                    const GeomState& gs, const uint32_t* point_list, const uint32_t* cull,
-                                    const ImageState& is, cudaStream_t st)
-{
-    constexpr int BATCH = 128;
-    const int gx = (v.width + TILE - 1) / TILE, gy = (v.height + TILE - 1) / TILE;
-    const size_t smem = BwdMma<NS4>::smem_bytes(BATCH);
-    if (gs.grad_row_floats != BwdMma<NS4>::ROWF) return cudaErrorInvalidValue;
-    auto kern = k_composite_bwd_mma<NS4, BATCH>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int sem_vec = (g.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.semantics) & 15) == 0);
-    kern<<<gx * gy, COMPOSITE_THREADS, smem, st>>>(
-        is.ranges, is.tile_order, point_list, cull, v.width, v.height, gx, gs.geo, gs.rgbd, g.semantics, g.S, sem_vec,
-        v.background, in.out_alpha, is.n_contrib, in.dL_dcolor, in.dL_dsemantic, in.dL_ddepth, in.dL_dalpha, gs.grad_rows);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -40,8 +40,8 @@ struct GeomState {
     size_t    sortp_temp_bytes;
     uint2*    rect;              // [P]
     float*    dopacity;          // [P]   dL/d(activated opacity) of one view when opacities are raw logits
-    float*    grad_rows;         // [P][grad_row_floats] per-Gaussian accumulators of the composite backward (S <= 16):
-                                 //       payload gradients + six pixel moments, see k_composite_bwd_mma
+    float*    grad_rows;         // [P][grad_row_floats] per-Gaussian accumulators of the composite backward (S <= 32):
+                                 //       payload gradients + six pixel moments, see k_composite_bwd_warp
     int       grad_row_floats;   // 0 = the direct-atomics backward is used for this channel count
     Meta*     meta;
     char*     scan_temp;

@@ -494,10 +494,10 @@ cudaError_t launch_preprocess_fwd(const goi_view& v, const goi_gaussians& g, int
 // Per-Gaussian backward: d(conic) -> d(cov2D) -> d(cov3D), d(mean) through the EWA Jacobian, the
 // projection, the depth and the SH view direction; d(cov3D) -> d(scale), d(quaternion).
 // ------------------------------------------------------------------------------------------------
-// Scratch rows of the tensor-core composite backward (k_composite_bwd_mma): per Gaussian 8 NT floats = the payload
+// Scratch rows of the tensor-core composite backward (k_composite_bwd_warp): per Gaussian 8 NT floats = the payload
 // gradients (r, g, b, depth, semantics) and the six pixel moments (M0, Mx, My, Mxx, Mxy, Myy) about rint(mean2D);
 // logical column c = 8 nt + n lives at float 2 NT (n >> 1) + 2 nt + (n & 1).  rows == NULL: the composite wrote
-// dL_dmean2D / dL_dconic / dL_dcolor / dL_ddepth / opacity itself (direct-atomics kernel, S > 16).
+// dL_dmean2D / dL_dconic / dL_dcolor / dL_ddepth / opacity itself (direct-atomics kernel, S > 32).
 struct GradRows {
     const float* rows;
     int rowf, nt;
