@@ -328,7 +328,21 @@ static int forward_render_impl(const goi_view* view, const goi_gaussians* g, con
     if ((rc = debug_sync(view, st, "binning")) != GOI_OK) return rc;
     {
         StageScope sc(ST_COMPOSITE_FWD, st);
-        if (mask) GOI_CUDA(launch_composite_fwd_mask(*view, *g, *out, *mask, gs, bs.vals[0], bs.vals[1], is, st), "composite forward + mask");
+        // The mask of a render whose semantic image is wanted anyway: the warp-autonomous composite followed by the
+        // tcgen05 mask kernel on the planar image beats the fused epilogue (1.40 vs 1.50 ms at c2) and equals
+        // goi_forward_auto + goi_mask bit for bit.  A mask-only render (out_semantic == NULL) keeps the fused kernel: it
+        // never writes or re-reads the [S,H,W] image.
+        goi_mask_args m2;
+        bool two_kernels = false;
+        if (mask && out->out_semantic && gs.grad_row_floats > 0) {
+            m2 = *mask;
+            m2.x = out->out_semantic; m2.stride_n = 1; m2.stride_c = (int64_t)view->width * view->height;
+            two_kernels = mask_uses_tensor_memory(m2);
+        }
+        if (two_kernels) {
+            GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], bs.cull8, bs.cull_plane, is, st), "composite forward");
+            GOI_CUDA(launch_mask_apply(m2, st), "mask");
+        } else if (mask) GOI_CUDA(launch_composite_fwd_mask(*view, *g, *out, *mask, gs, bs.vals[0], bs.vals[1], is, st), "composite forward + mask");
         else GOI_CUDA(launch_composite_fwd(*view, *g, *out, gs, bs.vals[0], bs.vals[1], gs.grad_row_floats > 0 ? bs.cull8 : nullptr,
                                            bs.cull_plane, is, st), "composite forward");
     }

@@ -129,6 +129,8 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewma
                                 cudaStream_t st);
 cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st);
 cudaError_t launch_mask_table(const goi_mask_args& a, cudaStream_t st);
+bool mask_uses_tensor_memory(const goi_mask_args& a);
+cudaError_t launch_mask_apply(const goi_mask_args& a, cudaStream_t st);   // the per-element kernel only (table already built)
 cudaError_t launch_mask_zero_input(const goi_mask_args& a, cudaStream_t st);   // x == 0 everywhere; table already built
 cudaError_t launch_composite_fwd_mask(const goi_view& v, const goi_gaussians& g, const goi_fwd_out& out,
                                       const goi_mask_args& m, const GeomState& gs, const uint32_t* point_list,

@@ -458,10 +458,16 @@ cudaError_t launch_mask_zero_input(const goi_mask_args& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
+// true = goi_mask on this problem runs the tcgen05 kernel (the render-then-mask route then beats the fused epilogue)
+bool mask_uses_tensor_memory(const goi_mask_args& a)
 {
-    cudaError_t e = launch_mask_table(a, st);
-    if (e != cudaSuccess) return e;
+    int KP, NP;
+    size_t smem;
+    return a.S > 0 && mask_tc_applicable(a, KP, NP, smem);
+}
+
+cudaError_t launch_mask_apply(const goi_mask_args& a, cudaStream_t st)
+{
     if (a.N <= 0) return cudaSuccess;
     {
         int KP, NP;
@@ -477,6 +483,13 @@ cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
         case 8: return launch_mask_t<8, 256>(a, st);
         default: return launch_mask_t<16, 256>(a, st);
     }
+}
+
+cudaError_t launch_mask(const goi_mask_args& a, cudaStream_t st)
+{
+    cudaError_t e = launch_mask_table(a, st);
+    if (e != cudaSuccess) return e;
+    return launch_mask_apply(a, st);
 }
 
 }  // namespace goi

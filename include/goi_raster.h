@@ -302,7 +302,10 @@ int goi_mask(const goi_mask_args* args, void* stream);
  * stride_c are ignored, mask->N must be width*height and mask->S == g->S > 0; sim / bg_mask / idx are
  * [H*W].  out->out_semantic may be NULL: the semantic image is then never written to memory (a
  * mask-only render saves its 4*S*N bytes of writes and the mask pass's 4*S*N bytes of reads).
- * Results are bit-identical to goi_forward_auto followed by goi_mask on its out_semantic. */
+ * With out_semantic given (and K = 300, S <= 32) the library runs the plain composite followed by the tcgen05 mask kernel
+ * on the planar image -- faster than the fused epilogue, and bit-identical to goi_forward_auto + goi_mask.  The fused
+ * epilogue (mask-only renders, other shapes) evaluates the same 3xTF32 projection with warp-level MMAs in another
+ * summation order: codebook rows can differ from goi_mask's only where the top two logits agree to ~1e-6. */
 int goi_forward_mask(const goi_view* view, const goi_gaussians* g, const goi_fwd_out* out,
                      const goi_mask_args* mask,
                      void* geom_buf, size_t geom_bytes, void* binning_buf, size_t binning_bytes,
