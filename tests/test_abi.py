@@ -90,6 +90,16 @@ def test_validation_errors_without_gpu():
     g = _C.goi_gaussians(0, 0, 0, 0, None, None, None, None, None, None, None, None)
     rc = L.goi_forward_prepare(C.byref(view), C.byref(g), None, None, 0, None, C.byref(R))
     assert rc == 0 and R.value == 0
+    # goi_forward_async: argument checks come before any CUDA call
+    g = _C.goi_gaussians(10, 16, 0, 0, 16, 16, None, None, 16, 16, 16, None)
+    out = _C.goi_fwd_out(16, None, 16, 16, 16)
+    status = (C.c_uint32 * 4)()
+    rc = L.goi_forward_async(C.byref(view), C.byref(g), C.byref(out), 16, 1 << 20, 16, 1 << 20, 0, 16, 1 << 20, None, status)
+    assert rc == -1 and b"capacity" in L.goi_last_error()
+    rc = L.goi_forward_async(C.byref(view), C.byref(g), C.byref(out), 16, 1 << 20, 16, 1 << 20, 1000, 16, 1 << 20, None, None)
+    assert rc == -1 and b"status_host" in L.goi_last_error()
+    rc = L.goi_forward_async(C.byref(view), C.byref(g), C.byref(out), 16, 1 << 20, 16, 64, 1_000_000, 16, 1 << 20, None, status)
+    assert rc == -3 and b"binning" in L.goi_last_error()
     # mask argument checks
     a = _C.goi_mask_args()
     a.N, a.S, a.K, a.D = 10, 0, 300, 256

@@ -93,3 +93,26 @@ def test_shard_views_partition():
         allv = sorted(v for r in range(world) for v in shard_views(64, r, world))
         assert allv == list(range(64))
     assert shard_views(3, 5, 8) == []
+
+
+def test_grad_arena_slots_are_aligned_and_only_aliased_grads_are_dropped():
+    """GradArena hands 16-byte-aligned slices to the C ABI whatever P is (P % 4 != 0 put the rotation slot
+    at an odd float offset), keeps its padding zero, and on entering the context drops only the `.grad`s that alias
+    the arena (a gradient left by other code must survive)."""
+    from goi_b200.view_parallel import GradArena
+    P = 1001
+    params = {"means3D": torch.zeros(P, 3, requires_grad=True), "opacities": torch.zeros(P, 1, requires_grad=True),
+              "scales": torch.zeros(P, 3, requires_grad=True), "rotations": torch.zeros(P, 4, requires_grad=True)}
+    arena = GradArena(params)
+    base = arena.flat.data_ptr()
+    for name, p in params.items():
+        off = (arena.slots[name].data_ptr() - base) // 4
+        assert off % 4 == 0 and arena.slots[name].numel() == p.numel(), name
+    assert arena.flat.numel() % 4 == 0 and float(arena.flat.abs().sum()) == 0.0
+    params["means3D"].grad = arena.slots["means3D"].view(P, 3)          # aliases the arena (left by the previous view)
+    foreign = torch.ones(P, 1)
+    params["opacities"].grad = foreign                                  # does not
+    arena.clear_grads(only_aliased=True)
+    assert params["means3D"].grad is None and params["opacities"].grad is foreign
+    arena.clear_grads()
+    assert params["opacities"].grad is None
