@@ -17,10 +17,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "lib", "libgoi_raster.so")
-LIB_SEMLOSS = os.path.join(HERE, "lib", "libgoi_semloss.so")      # fused training loss (links cuBLAS for its two plain GEMMs)
+LIB_SEMLOSS = os.path.join(HERE, "lib", "libgoi_semloss.so")      # fused training loss (its own tcgen05 GEMMs: no library dependency)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "composite_fwd.cu", "composite_bwd.cu", "mask.cu"]
-HEADERS = [os.path.join(CSRC, "goi_internal.cuh"), os.path.join(CSRC, "goi_cull.cuh"),
+HEADERS = [os.path.join(CSRC, "goi_internal.cuh"), os.path.join(CSRC, "goi_cull.cuh"), os.path.join(CSRC, "semloss_tc.cuh"),
            os.path.join(HERE, "..", "include", "goi_raster.h"), os.path.join(HERE, "..", "include", "goi_semloss.h")]
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -66,14 +66,12 @@ def build(force: bool = False, verbose: bool = False, stats: bool = False) -> st
 
 
 def build_semloss(force: bool = False, verbose: bool = False) -> str:
-    """libgoi_semloss.so: csrc/semloss.cu + cuBLAS (dynamic, soname libcublas.so.12: the copy torch already loaded, or
-    the toolkit's via the rpath).  Kept apart from libgoi_raster.so so the rasterizer stays dependency-free."""
+    """libgoi_semloss.so: csrc/semloss.cu + csrc/semloss_tc.cuh (static CUDA runtime; no cuBLAS -- both contractions of
+    the loss are hand-written tcgen05 kernels).  Kept apart from libgoi_raster.so: a trainer-side library."""
     obj = _compile("semloss.cu", force, verbose)
     if force or _stale(LIB_SEMLOSS, [obj]):
-        cuda_lib = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(NVCC))), "lib64")
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-Xcompiler", "-fPIC", obj, "-o", LIB_SEMLOSS, f"-L{cuda_lib}", "-lcublas",
-               "-Xlinker", f"-rpath={cuda_lib}"]
+               "-Xcompiler", "-fPIC", obj, "-o", LIB_SEMLOSS]
         subprocess.run(cmd, check=True)
     return LIB_SEMLOSS
 

@@ -2,26 +2,27 @@
 // section 8 row f2).  Replaces the torch chain of the reference's train.py:142-167 and its autograd backward.
 //
 // Data flow (N pixels, K codebook rows, D codebook width, S rendered channels):
-//     lut1 = lut / |lut|                          k_lut_normalize            K blocks
-//     inv[p] = 1 / |gt[p]|                        k_gt_inv_norms             one read of gt (4 N D bytes)
-//     G = gt @ lut1^T                             cuBLAS GEMM                (plain library GEMM, fp32 or TF32)
-//     per pixel, one pass                         k_semloss_rows             reads G (4NK) + x (4NS), writes dsim over G
-//         sim = G * inv;  z = W x + b;  P' = softmax(z);  k^ = argmax z
+//     lut1 = lut / |lut|                          k_lut_normalize, k_build_wimg   K blocks; TF32 hi / lo operand images
+//     k^ = argmax (W x + b)                       k_semloss_zarg             reads x (4NS)
+//     sim = (gt / |gt|) @ lut1^T  in TMEM         k_sim_tc (semloss_tc.cuh)  tcgen05.mma, 3 x TF32 = fp32-accurate;
 //         smax, k* = max/argmax sim;  L = (sim == smax);  P = softmax(t sim);  E = sum P log P
-//         loss partials: sum (P'-L)^2, smax, E, sim[k^]
+//         loss partials: smax, E, sim[k^]
+//         dsim = -(1/N)([k=k*] + [k=k^]) - (0.3 t / N) P (log P - E)   -> dsimT (pre-scaled by 1/|gt|), label bits L
+//         reads gt once (4ND), writes dsimT (4NK) + L (N K / 8): sim itself never reaches HBM
+//     per pixel, one pass                         k_semloss_rows             reads x (4NS) + L
+//         z = W x + b;  P' = softmax(z);  loss partial sum (P'-L)^2
 //         dz = P' (g - P'.g), g = 100/(NK) (P'-L)          -> dL/dx = dz W, dL/dW += dz x^T, dL/db += dz
-//         dsim = -(1/N)([k=k*] + [k=k^]) - (0.3 t / N) P (log P - E);   G <- dsim * inv
-//     dlut1 = (dsim*inv)^T @ gt                   cuBLAS GEMM
+//     dlut1 = dsim^T @ gt  accumulated in TMEM    k_dlut_tc (semloss_tc.cuh) reads dsimT + gt (per 128-wide slice)
 //     dlut = (dlut1 - (dlut1.lut1) lut1) / |lut|  k_lut_normalize_bwd
-// HBM roofline of the hand-written part: 4N(2K + 2S + 1) + 4ND bytes; the row kernel is FP32-FMA bound
-// (3 x K x S FMA per pixel for logits, dx and dW) next to that.
+// No library GEMM: both contractions are hand-written tcgen05 kernels.  HBM roofline: 4N(2D + 2K + 2S) bytes per slice
+// pair; the row kernel is FP32-FMA bound (3 x K x S FMA per pixel for logits, dx and dW) next to that.
 #include <cuda_runtime.h>
-#include <cublas_v2.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <mutex>
 #include "../../include/goi_semloss.h"
+#include "semloss_tc.cuh"
 
 static_assert(sizeof(goi_semloss_args) == 152, "goi_semloss_args layout is part of the ABI (ctypes mirror)");
 
@@ -42,12 +43,10 @@ constexpr int ROWS_THREADS = 256;
 constexpr int PB = 32;                 // pixels per CTA batch (4 per warp)
 
 struct Accum {                         // double accumulators of the loss terms + the min (ordered-int encoded)
-    double lab, simval, ent, rec;
-    int min_simval_key;
-    int pad;
+    double lab;                        // k_semloss_rows
+    tc5::SimStats sim;                 // k_sim_tc: simval, ent, rec, min_simval_key
 };
 
-__device__ __forceinline__ int float_key(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float key_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -102,29 +101,6 @@ __global__ void __launch_bounds__(128) k_lut_normalize_bwd(int K, int D, const f
     for (int d = threadIdx.x; d < D; d += blockDim.x) dlut[(size_t)k * D + d] = (g[d] - dt * u[d]) * inv;
 }
 
-// inv[p] = 1 / |gt[p]|.  Row-major [N,D]: one warp per row, coalesced.  Planar [D,N]: one thread per pixel.
-__global__ void __launch_bounds__(256) k_gt_inv_norms(int64_t N, int D, int planar, const float* __restrict__ gt,
-                                                      float* __restrict__ inv)
-{
-    if (planar) {
-        for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
-            float n2 = 0.f;
-            for (int d = 0; d < D; ++d) { const float v = gt[(size_t)d * N + p]; n2 = fmaf(v, v, n2); }
-            inv[p] = 1.f / sqrtf(n2);
-        }
-    } else {
-        const int lane = threadIdx.x & 31;
-        const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < N; p += warps) {
-            const float* r = gt + (size_t)p * D;
-            float n2 = 0.f;
-            for (int d = lane; d < D; d += 32) n2 = fmaf(r[d], r[d], n2);
-            n2 = warp_sum(n2);
-            if (lane == 0) inv[p] = 1.f / sqrtf(n2);
-        }
-    }
-}
-
 // Warp-wide sums of N per-lane partial values with a transposing butterfly: while more than one value is left,
 // a step at lane distance `off` exchanges halves (lanes with bit `off` set keep the upper half) -- N/2 + N/4 + ...
 // shuffles -- and the remaining steps are plain all-reduce steps on the single survivor.  N = 32: 31 shuffles,
@@ -154,16 +130,67 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane)
 }
 __device__ __forceinline__ int dx_channel(int lane, int n) { return n == 32 ? lane : (lane >> 1); }
 
-// One pass per pixel over its similarity row; see the header of this file.
+// k^ = argmax_k (W x + b)_k per pixel (first maximum, like torch.argmax): the codebook row train.py:156 looks up.  A
+// warp owns a pixel, lane l owns codebook rows l, l + 32, ...; weights staged once per CTA (rows padded with bias -inf).
+template <int NS4, int KI>
+__global__ void __launch_bounds__(ROWS_THREADS, 2)
+k_semloss_zarg(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
+               const float* __restrict__ W, const float* __restrict__ bias, int* __restrict__ zarg)
+{
+    constexpr int SP = 4 * NS4, WS = SP + 4, KP = 32 * KI;
+    extern __shared__ float4 smem4[];
+    float* s_w = reinterpret_cast<float*>(smem4);               // [KP][WS]
+    float* s_b = s_w + (size_t)KP * WS;                         // [KP]
+    float* s_x = s_b + KP;                                      // [8 warps][2][SP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < KP * SP; i += ROWS_THREADS) {
+        const int k = i / SP, c = i % SP;
+        s_w[k * WS + c] = (k < K && c < S) ? W[(size_t)k * S + c] : 0.f;
+    }
+    for (int i = tid; i < KP; i += ROWS_THREADS) s_b[i] = i < K ? (bias ? bias[i] : 0.f) : -INFINITY;
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * (ROWS_THREADS / 32);
+    int par = 0;
+    for (int64_t p = (int64_t)blockIdx.x * (ROWS_THREADS / 32) + warp; p < N; p += nwarps, par ^= 1) {
+        float* xrow = s_x + (warp * 2 + par) * SP;              // double-buffered: no second __syncwarp per pixel
+        for (int c = lane; c < SP; c += 32) xrow[c] = c < S ? x[p * xs_n + c * xs_c] : 0.f;
+        __syncwarp();
+        float xs[SP];
+#pragma unroll
+        for (int q = 0; q < NS4; ++q) {
+            const float4 v = reinterpret_cast<const float4*>(xrow)[q];
+            xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+        }
+        float zmax = -INFINITY;
+        int za = 0;
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+            const int k = lane + 32 * i;
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < NS4; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
+                a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
+            }
+            a += s_b[k];
+            if (a > zmax) { zmax = a; za = k; }
+        }
+        warp_argmax(zmax, za);
+        if (lane == 0) zarg[p] = za;
+    }
+}
+
+// One pass per pixel over its logit row; see the header of this file.
 // Phase A: a warp owns a pixel, lane l owns codebook rows k = l, l+32, ... (KI values per lane, in registers); the
-//          next pixel's similarity row is prefetched while the current one is processed.
+//          next pixel's label bits are prefetched while the current one is processed.
 // Phase B: the CTA turns the PB staged dz rows into its running dW / db accumulators (thread t owns rows t, t+256).
-// exp/log are ex2/lg2.approx (2 ulp): they produce softmax weights that enter sums of K terms; decisions (arg-max,
-// label equality) never depend on them.
+// exp is ex2.approx (2 ulp): it produces softmax weights that enter sums of K terms; decisions never depend on it.
+// (The expression order of z, P', dz, dx, dW below is the one of the single-pass kernel of round 1: same numerics.)
 template <int NS4, int KI>
 __global__ void __launch_bounds__(ROWS_THREADS, (NS4 <= 4 ? 2 : 1))
-k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
-               float* __restrict__ G, const float* __restrict__ inv_norm, const float* __restrict__ W,
+k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
+               const uint32_t* __restrict__ lmask, int64_t Npad, int KW, const float* __restrict__ W,
                const float* __restrict__ bias, float* __restrict__ dL_dx, float* __restrict__ dW,
                float* __restrict__ db, Accum* __restrict__ acc_out)
 {
@@ -174,8 +201,7 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
     constexpr int PPW = PB / 8;                 // pixels per warp per batch
     extern __shared__ float4 smem4[];
     // Codebook rows are padded to KP = 32 KI with zero weights and a bias of -inf: a padded row has logit -inf,
-    // softmax weight 0 and gradient 0, so the per-lane loops below run without any k < K control flow (the guards
-    // cost more issue slots than the arithmetic they protected in the r01f capture).
+    // softmax weight 0 and gradient 0, so the per-lane loops below run without any k < K control flow.
     constexpr int KP = 32 * KI;
     float* s_w = reinterpret_cast<float*>(smem4);               // [KP][WS]
     float* s_b = s_w + (size_t)KP * WS;                         // [KP]
@@ -190,9 +216,7 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
     for (int i = tid; i < KP; i += ROWS_THREADS) s_b[i] = i < K ? (bias ? bias[i] : 0.f) : -INFINITY;
     __syncthreads();
 
-    const float invN = 1.0f / (float)N;
     const float cl = 100.0f / ((float)N * (float)K);            // d(50 * MSE)/d(P') = 2 * 50 / (N K) * (P' - L)
-    const float ce = 0.3f * t_anneal * invN;
 
     float accw[KTT][SP], accb[KTT];
 #pragma unroll
@@ -201,19 +225,13 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
 #pragma unroll
         for (int c = 0; c < SP; ++c) accw[kk][c] = 0.f;
     }
-    double l_lab = 0.0, l_sim = 0.0, l_ent = 0.0, l_rec = 0.0;
-    float l_min = INFINITY;
+    double l_lab = 0.0;
 
     const int64_t nbatch = (N + PB - 1) / PB;
-    // prefetch registers: raw similarity row + 1/|gt| of the warp's next pixel
-    float gn[KI], invn = 0.f;
+    // prefetch register: word `lane` of the next pixel's label bits (word i covers codebook rows 32 i .. 32 i + 31)
+    uint32_t lw = 0;
     auto prefetch = [&](int64_t p) {
-        if (p < N) {
-            invn = inv_norm[p];
-            const float* r = G + (size_t)p * K;
-#pragma unroll
-            for (int i = 0; i < KI; ++i) gn[i] = (lane + 32 * i < K) ? r[lane + 32 * i] : 0.f;
-        }
+        lw = (p < N && lane < KW) ? __ldg(lmask + (size_t)lane * Npad + (size_t)p) : 0u;
     };
     prefetch((int64_t)blockIdx.x * PB + warp * PPW);
 
@@ -232,11 +250,10 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
                 continue;
             }
             for (int c = lane; c < SP; c += 32) xrow[c] = c < S ? x[p * xs_n + c * xs_c] : 0.f;
-            // this pixel's prefetched row -> sim (padded rows: -inf), then start the next pixel's loads
-            float sm[KI];
-            const float inv = invn;
+            // label bits of this lane's codebook rows: bit i <-> row lane + 32 i
+            unsigned lmask_l = 0;
 #pragma unroll
-            for (int i = 0; i < KI; ++i) sm[i] = (lane + 32 * i < K) ? gn[i] * inv : -INFINITY;
+            for (int i = 0; i < KI; ++i) lmask_l |= ((__shfl_sync(0xffffffffu, lw, i) >> lane) & 1u) << i;
             prefetch(pnext);
             __syncwarp();
             float xs[SP];
@@ -245,12 +262,10 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
                 const float4 v = reinterpret_cast<const float4*>(xrow)[q];
                 xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
             }
-            float* grow = G + (size_t)p * K;
 
-            // logits of this lane's codebook rows; row maxima with the FIRST index on ties
+            // logits of this lane's codebook rows and their maximum
             float z[KI];
-            float zmax = -INFINITY, smax = -INFINITY;
-            int zarg = 0, sarg = 0;
+            float zmax = -INFINITY;
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
                 const int k = lane + 32 * i;
@@ -262,54 +277,35 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
                     a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
                 }
                 z[i] = a + s_b[k];
-                if (z[i] > zmax) { zmax = z[i]; zarg = k; }              // ascending k: first maximum wins
-                if (sm[i] > smax) { smax = sm[i]; sarg = k; }
+                zmax = fmaxf(zmax, z[i]);
                 asm volatile("" ::: "memory");                   // keep the weight loads of later rows from piling up in registers
             }
-            warp_argmax(zmax, zarg);
-            warp_argmax(smax, sarg);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
 
-            // softmax numerators, computed once: z <- exp(z - zmax), pa <- exp(t (sim - smax)); label bits
-            float pa[KI];
-            float zsum = 0.f, asum = 0.f;
-            unsigned lmask = 0;
+            // softmax numerators, computed once: z <- exp(z - zmax)
+            float zsum = 0.f;
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
-                const float a = t_anneal * (sm[i] - smax);
-                lmask |= (sm[i] == smax) ? (1u << i) : 0u;
                 z[i] = __expf(z[i] - zmax);                      // padded rows: exp(-inf) = 0
-                pa[i] = __expf(a);
-                sm[i] = a;                                       // sim itself is no longer needed: keep t (sim - smax)
                 zsum += z[i];
-                asum += pa[i];
             }
             zsum = warp_sum(zsum);
-            asum = warp_sum(asum);
-            const float zinv = 1.f / zsum, logZ = __logf(asum), ainv = 1.f / asum;
-            // E = sum P log P, lab = sum (P' - L)^2, dot = sum P' g, rec = t (sim[argmax z] - smax)
-            float E = 0.f, lab = 0.f, dot = 0.f, rec = 0.f;
+            const float zinv = 1.f / zsum;
+            // lab = sum (P' - L)^2, dot = sum P' g
+            float lab = 0.f, dot = 0.f;
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
-                const int k = lane + 32 * i;
-                const float P = pa[i] * ainv;
-                const float logP = (k < K) ? sm[i] - logZ : 0.f;       // (0 * -inf of a padded row would be NaN)
-                E = fmaf(P, logP, E);
                 const float Pz = z[i] * zinv;
-                const float diff = Pz - ((lmask & (1u << i)) ? 1.f : 0.f);
+                const float diff = Pz - ((lmask_l & (1u << i)) ? 1.f : 0.f);
                 lab = fmaf(diff, diff, lab);
                 dot = fmaf(Pz, cl * diff, dot);
-                rec = (k == zarg) ? sm[i] : rec;
-                z[i] = Pz; pa[i] = P; sm[i] = logP;
+                z[i] = Pz;
             }
-            E = warp_sum(E); lab = warp_sum(lab); dot = warp_sum(dot); rec = warp_sum(rec);
-            if (lane == 0) {
-                // rec holds t (sim[k^] - smax): undo the shift and scale
-                l_lab += (double)lab; l_sim += (double)smax; l_ent += (double)E;
-                l_rec += (double)(rec / t_anneal + smax);
-                l_min = fminf(l_min, smax);
-            }
+            lab = warp_sum(lab); dot = warp_sum(dot);
+            if (lane == 0) l_lab += (double)lab;
 
-            // gradients: dz -> staged row + dx partials; dsim (pre-scaled by 1/|gt|) overwrites G
+            // gradients: dz -> staged row + dx partials
             float dxp[DXN];
 #pragma unroll
             for (int c = 0; c < DXN; ++c) dxp[c] = 0.f;
@@ -317,12 +313,8 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
             for (int i = 0; i < KI; ++i) {
                 const int k = lane + 32 * i;
                 const float Pz = z[i];
-                const float dz = Pz * (cl * (Pz - ((lmask & (1u << i)) ? 1.f : 0.f)) - dot);   // 0 for padded rows
+                const float dz = Pz * (cl * (Pz - ((lmask_l & (1u << i)) ? 1.f : 0.f)) - dot);   // 0 for padded rows
                 dzrow[k] = dz;
-                float ds = -ce * pa[i] * (sm[i] - E);
-                ds -= (k == sarg) ? invN : 0.f;
-                ds -= (k == zarg) ? invN : 0.f;
-                if (k < K) grow[k] = ds * inv;
 #pragma unroll
                 for (int q = 0; q < NS4; ++q) {
                     const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
@@ -372,39 +364,60 @@ k_semloss_rows(int64_t N, int S, int K, float t_anneal, const float* __restrict_
             }
         }
     }
-    if (lane == 0) {
-        atomicAdd(&acc_out->lab, l_lab);
-        atomicAdd(&acc_out->simval, l_sim);
-        atomicAdd(&acc_out->ent, l_ent);
-        atomicAdd(&acc_out->rec, l_rec);
-        if (l_min < INFINITY) atomicMin(&acc_out->min_simval_key, float_key(l_min));
-    }
+    if (lane == 0) atomicAdd(&acc_out->lab, l_lab);
 }
 
 __global__ void k_semloss_init(Accum* acc)
 {
-    acc->lab = acc->simval = acc->ent = acc->rec = 0.0;
-    acc->min_simval_key = 0x7fffffff;
-    acc->pad = 0;
+    acc->lab = acc->sim.simval = acc->sim.ent = acc->sim.rec = 0.0;
+    acc->sim.min_simval_key = 0x7fffffff;
+    acc->sim.pad = 0;
 }
 
 __global__ void k_semloss_finalize(int64_t N, int K, const Accum* acc, float* losses)
 {
     const double n = (double)N;
     const double lab = 50.0 * acc->lab / (n * (double)K);
-    const double sl = 1.0 - acc->simval / n;
-    const double sl1 = -acc->ent / n;
-    const double recc = 1.0 - acc->rec / n;
+    const double sl = 1.0 - acc->sim.simval / n;
+    const double sl1 = -acc->sim.ent / n;
+    const double recc = 1.0 - acc->sim.rec / n;
     losses[0] = (float)(lab + sl + 0.3 * sl1 + recc);
     losses[1] = (float)lab; losses[2] = (float)sl; losses[3] = (float)sl1; losses[4] = (float)recc;
-    losses[5] = key_float(acc->min_simval_key);
+    losses[5] = key_float(acc->sim.min_simval_key);
     losses[6] = 0.f; losses[7] = 0.f;
 }
 
-// ---- workspace carving ------------------------------------------------------------------------
+// ---- problem geometry of the tensor-core kernels and workspace carving ------------------------------------------
+struct Geometry {
+    int NP;            // codebook rows padded to 16 accumulator columns
+    int KC;            // reduction elements per staged chunk: 32, or 16 when the codebook is longer than 304 rows
+    int sbo;           // bytes between 8-row groups of an operand image
+    int nchunks;       // chunks of the codebook width (k_sim_tc)
+    int wbytes;        // one codebook image of one chunk
+    int KW;            // label words per pixel
+    int64_t ntiles, Npad;
+    size_t smem;       // dynamic shared memory of either kernel
+};
+Geometry geometry(int64_t N, int K, int D)
+{
+    Geometry g{};
+    g.NP = ((K + 15) / 16) * 16;
+    g.KC = g.NP <= 304 ? 32 : 16;
+    g.sbo = tc5::sbo_for(g.KC);
+    g.nchunks = (D + g.KC - 1) / g.KC;
+    g.wbytes = (g.NP / 8) * g.sbo;
+    g.KW = (g.NP + 31) / 32;
+    g.ntiles = (N + 127) / 128;
+    g.Npad = g.ntiles * 128;
+    g.smem = (size_t)4 * g.wbytes + (size_t)4 * 16 * g.sbo;
+    return g;
+}
+
 struct Workspace {
-    float* G;          // [N,K]
-    float* inv_norm;   // [N]
+    float* dsimT;      // [ntiles][NP][128]  d loss / d sim * (1 / |gt|), pixel-minor per tile
+    uint32_t* lmask;   // [KW][Npad]         label bits (sim == row max)
+    int* zarg;         // [N]                argmax of the MLP logits
+    uint8_t* wimg;     // [nchunks][hi, lo][wbytes]   codebook operand images
     float* lut1;       // [K,D]
     float* lut_norm;   // [K]
     float* dlut1;      // [K,D]
@@ -413,11 +426,14 @@ struct Workspace {
 };
 Workspace carve(char* base, int64_t N, int K, int D)
 {
+    const Geometry g = geometry(N, K, D);
     Workspace w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
-    w.G = (float*)take(sizeof(float) * (size_t)N * K);
-    w.inv_norm = (float*)take(sizeof(float) * (size_t)N);
+    w.dsimT = (float*)take(sizeof(float) * (size_t)g.ntiles * g.NP * 128);
+    w.lmask = (uint32_t*)take(sizeof(uint32_t) * (size_t)g.KW * g.Npad);
+    w.zarg = (int*)take(sizeof(int) * (size_t)N);
+    w.wimg = (uint8_t*)take((size_t)g.nchunks * 2 * g.wbytes);
     w.lut1 = (float*)take(sizeof(float) * (size_t)K * D);
     w.lut_norm = (float*)take(sizeof(float) * (size_t)K);
     w.dlut1 = (float*)take(sizeof(float) * (size_t)K * D);
@@ -426,42 +442,95 @@ Workspace carve(char* base, int64_t N, int K, int D)
     return w;
 }
 
-// One cuBLAS handle per device, created on first use (cublasCreate costs milliseconds and allocates); calls are
-// serialised on it because the stream is a property of the handle.
-std::mutex g_mu;
-cublasHandle_t g_handle[64] = {nullptr};
-
 int sem_groups(int S) { return S <= 4 ? 1 : S <= 8 ? 2 : S <= 12 ? 3 : S <= 16 ? 4 : 8; }
-
-template <int NS4, int KI>
-cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, cudaStream_t st)
+int device_sms()
 {
-    constexpr int SP = 4 * NS4;
-    constexpr int KP = 32 * KI;                                 // padded codebook rows (see the kernel)
-    const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + PB * SP + (size_t)PB * KP);
-    auto kern = k_semloss_rows<NS4, KI>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+template <int KC, bool PLANAR>
+cudaError_t launch_sim_t(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
+{
+    auto kern = tc5::k_sim_tc<KC, PLANAR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    const int sms = device_sms();
+    const unsigned grid = (unsigned)(g.ntiles < sms ? g.ntiles : sms);
+    kern<<<grid, tc5::THREADS, g.smem, st>>>(a.N, a.D, a.K, g.NP, g.nchunks, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
+                                             a.anneal_t, a.gt, w.wimg, w.zarg, w.dsimT, w.lmask, g.Npad, &w.acc->sim);
+    return cudaGetLastError();
+}
+cudaError_t launch_sim(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
+{
+    if (g.KC == 32) return a.gt_planar ? launch_sim_t<32, true>(a, w, g, st) : launch_sim_t<32, false>(a, w, g, st);
+    return a.gt_planar ? launch_sim_t<16, true>(a, w, g, st) : launch_sim_t<16, false>(a, w, g, st);
+}
+
+template <int KC, bool PLANAR>
+cudaError_t launch_dlut_t(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
+{
+    auto kern = tc5::k_dlut_tc<KC, PLANAR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    const int sms = device_sms();
+    const int n_slices = (a.D + 127) / 128;
+    int64_t n_ranges = sms / n_slices;                          // CTAs of one pixel range sit next to each other: they
+    if (n_ranges < 1) n_ranges = 1;                             // read the same dsimT tiles at about the same time (L2)
+    if (n_ranges > g.ntiles) n_ranges = g.ntiles;
+    kern<<<(unsigned)(n_ranges * n_slices), tc5::THREADS, g.smem, st>>>(a.N, a.D, a.K, g.NP, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
+                                                                       n_slices, a.gt, w.dsimT, w.dlut1);
+    return cudaGetLastError();
+}
+cudaError_t launch_dlut(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
+{
+    if (g.KC == 32) return a.gt_planar ? launch_dlut_t<32, true>(a, w, g, st) : launch_dlut_t<32, false>(a, w, g, st);
+    return a.gt_planar ? launch_dlut_t<16, true>(a, w, g, st) : launch_dlut_t<16, false>(a, w, g, st);
+}
+
+template <int NS4, int KI>
+cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
+{
+    constexpr int SP = 4 * NS4;
+    constexpr int KP = 32 * KI;                                 // padded codebook rows (see the kernel)
+    const int sms = device_sms();
+    {
+        const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + 16 * SP);
+        auto kern = k_semloss_zarg<NS4, KI>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int64_t grid = (a.N + 7) / 8;
+        if (grid > (int64_t)sms * 2) grid = (int64_t)sms * 2;
+        kern<<<(unsigned)grid, ROWS_THREADS, smem, st>>>(a.N, a.S, a.K, a.x, a.x_stride_n, a.x_stride_c, a.mlp_weight,
+                                                        a.mlp_bias, w.zarg);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = launch_sim(a, w, g, st);
+    if (e != cudaSuccess) return e;
+    const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + PB * SP + (size_t)PB * KP);
+    auto kern = k_semloss_rows<NS4, KI>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int64_t nbatch = (a.N + PB - 1) / PB;
     int64_t grid = (int64_t)sms * (NS4 <= 4 ? 2 : 1);
     if (grid > nbatch) grid = nbatch;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, ROWS_THREADS, smem, st>>>(a.N, a.S, a.K, a.anneal_t, a.x, a.x_stride_n, a.x_stride_c, w.G,
-                                                    w.inv_norm, a.mlp_weight, a.mlp_bias, a.dL_dx, a.dL_dmlp_weight,
+    kern<<<(unsigned)grid, ROWS_THREADS, smem, st>>>(a.N, a.S, a.K, a.x, a.x_stride_n, a.x_stride_c, w.lmask, g.Npad, g.KW,
+                                                    a.mlp_weight, a.mlp_bias, a.dL_dx, a.dL_dmlp_weight,
                                                     a.dL_dmlp_bias, w.acc);
     return cudaGetLastError();
 }
 
 template <int NS4>
-cudaError_t launch_rows(const goi_semloss_args& a, const Workspace& w, cudaStream_t st)
+cudaError_t launch_rows(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
 {
     // lanes own ceil(K / 32) codebook rows: 10 covers the reference's K = 300 without wasted unrolled iterations
-    if (a.K <= 160) return launch_rows_t<NS4, 5>(a, w, st);
-    if (a.K <= 320) return launch_rows_t<NS4, 10>(a, w, st);
-    return launch_rows_t<NS4, 16>(a, w, st);
+    if (a.K <= 160) return launch_rows_t<NS4, 5>(a, w, g, st);
+    if (a.K <= 320) return launch_rows_t<NS4, 10>(a, w, g, st);
+    return launch_rows_t<NS4, 16>(a, w, g, st);
 }
 
 }  // namespace
@@ -477,8 +546,6 @@ size_t goi_semloss_workspace_bytes(int64_t N, int32_t K, int32_t D)
 
 #define SL_CUDA(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(ERR_CUDA, "%s: %s", what, cudaGetErrorString(e_)); } while (0)
-#define SL_BLAS(call, what) do { cublasStatus_t s_ = (call); if (s_ != CUBLAS_STATUS_SUCCESS) \
-    return fail(ERR_CUDA, "%s: cuBLAS status %d", what, (int)s_); } while (0)
 
 int goi_semantic_loss(const goi_semloss_args* a, void* stream)
 {
@@ -486,7 +553,7 @@ int goi_semantic_loss(const goi_semloss_args* a, void* stream)
     if (a->N <= 0 || a->S <= 0 || a->K <= 0 || a->D <= 0) return fail(ERR_INVALID, "bad N/S/K/D");
     if (a->K > GOI_SEMLOSS_MAX_K) return fail(ERR_UNSUPPORTED, "K=%d > %d", a->K, GOI_SEMLOSS_MAX_K);
     if (a->S > 32) return fail(ERR_UNSUPPORTED, "S=%d > 32 semantic channels is not built for the loss kernel", a->S);
-    if (a->N >= ((int64_t)1 << 31) / 2) return fail(ERR_UNSUPPORTED, "N too large for 32-bit GEMM dimensions");
+    if (a->N >= ((int64_t)1 << 31) / 2) return fail(ERR_UNSUPPORTED, "N too large for 32-bit pixel indices");
     if (a->precision != GOI_SEMLOSS_FP32 && a->precision != GOI_SEMLOSS_TF32) return fail(ERR_INVALID, "bad precision");
     if (!a->x || !a->gt || !a->mlp_weight || !a->lut || !a->losses || !a->workspace)
         return fail(ERR_INVALID, "null pointers");
@@ -496,46 +563,30 @@ int goi_semantic_loss(const goi_semloss_args* a, void* stream)
     if (((uintptr_t)a->workspace & 255) != 0) return fail(ERR_WORKSPACE, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const Workspace w = carve((char*)a->workspace, a->N, a->K, a->D);
-    const int N = (int)a->N, K = a->K, D = a->D;
-
-    int dev = 0;
-    SL_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
-    if (dev < 0 || dev >= 64) return fail(ERR_UNSUPPORTED, "device index %d", dev);
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_handle[dev]) SL_BLAS(cublasCreate(&g_handle[dev]), "cublasCreate");
-    cublasHandle_t h = g_handle[dev];
-    SL_BLAS(cublasSetStream(h, st), "cublasSetStream");
-    SL_BLAS(cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST), "cublasSetPointerMode");
-    const cublasComputeType_t ct = a->precision == GOI_SEMLOSS_TF32 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
-    const float one = 1.f, zero = 0.f;
+    const Geometry g = geometry(a->N, a->K, a->D);
+    const int K = a->K, D = a->D;
 
     k_semloss_init<<<1, 1, 0, st>>>(w.acc);
     k_lut_normalize<<<K, 128, 0, st>>>(K, D, a->lut, w.lut1, w.lut_norm);
-    k_gt_inv_norms<<<148 * 8, 256, 0, st>>>(a->N, D, a->gt_planar, a->gt, w.inv_norm);
+    tc5::k_build_wimg<<<148, 256, 0, st>>>(K, D, g.NP, g.KC, g.nchunks, g.sbo, w.lut1, w.wimg);
     SL_CUDA(cudaGetLastError(), "prologue kernels");
     if (a->dL_dmlp_weight) SL_CUDA(cudaMemsetAsync(a->dL_dmlp_weight, 0, sizeof(float) * (size_t)K * a->S, st), "zero dW");
     if (a->dL_dmlp_bias) SL_CUDA(cudaMemsetAsync(a->dL_dmlp_bias, 0, sizeof(float) * (size_t)K, st), "zero db");
 
-    // G (row-major [N,K]) = gt @ lut1^T.  Column-major view: C[K x N] = lut1'[K x D] * gt'[D x N].
-    SL_BLAS(cublasGemmEx(h, CUBLAS_OP_T, a->gt_planar ? CUBLAS_OP_T : CUBLAS_OP_N, K, N, D, &one,
-                         w.lut1, CUDA_R_32F, D, a->gt, CUDA_R_32F, a->gt_planar ? N : D, &zero,
-                         w.G, CUDA_R_32F, K, ct, CUBLAS_GEMM_DEFAULT), "similarity GEMM");
-
+    // arg-max of the logits -> similarity GEMM + its row pass on the tensor cores -> the logit-side row pass
     cudaError_t e;
     switch (sem_groups(a->S)) {
-        case 1: e = launch_rows<1>(*a, w, st); break;
-        case 2: e = launch_rows<2>(*a, w, st); break;
-        case 3: e = launch_rows<3>(*a, w, st); break;
-        case 4: e = launch_rows<4>(*a, w, st); break;
-        default: e = launch_rows<8>(*a, w, st); break;
+        case 1: e = launch_rows<1>(*a, w, g, st); break;
+        case 2: e = launch_rows<2>(*a, w, g, st); break;
+        case 3: e = launch_rows<3>(*a, w, g, st); break;
+        case 4: e = launch_rows<4>(*a, w, g, st); break;
+        default: e = launch_rows<8>(*a, w, g, st); break;
     }
-    SL_CUDA(e, "row kernel");
+    SL_CUDA(e, "row kernels");
 
     if (a->dL_dlut) {
-        // dlut1 (row-major [K,D]) = dsim^T @ gt.  Column-major view: C[D x K] = gt'[D x N] * dsim'[N x K].
-        SL_BLAS(cublasGemmEx(h, a->gt_planar ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_T, D, K, N, &one,
-                             a->gt, CUDA_R_32F, a->gt_planar ? N : D, w.G, CUDA_R_32F, K, &zero,
-                             w.dlut1, CUDA_R_32F, D, ct, CUBLAS_GEMM_DEFAULT), "codebook-gradient GEMM");
+        SL_CUDA(cudaMemsetAsync(w.dlut1, 0, sizeof(float) * (size_t)K * D, st), "zero dlut1");
+        SL_CUDA(launch_dlut(*a, w, g, st), "codebook-gradient kernel");
         k_lut_normalize_bwd<<<K, 128, 0, st>>>(K, D, w.lut1, w.lut_norm, w.dlut1, a->dL_dlut);
     }
     k_semloss_finalize<<<1, 1, 0, st>>>(a->N, K, w.acc, a->losses);

@@ -1,0 +1,563 @@
+// semloss_tc.cuh -- the two dense contractions of the training-side semantic loss (reference train.py:150 and its
+// autograd backward) on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory), fp32-accurate
+// through the x = hi + lo TF32 split (three products, small terms first; ~2^-21 of an fp32 FMA chain).
+//
+//   k_sim_tc     sim = (gt / |gt|) @ lut1^T  for 128 pixels x all K codebook rows per tile, accumulated in TMEM over
+//                chunks of KC codebook-width elements, and -- while the row is still in tensor memory -- everything
+//                train.py:152-160 does with it: row max / arg-max / label bits, softmax(t sim) entropy, the loss
+//                partial sums and d loss / d sim.  The similarity matrix itself never reaches HBM; 1/|gt| is
+//                accumulated from the operand tiles as they are staged (no separate pass over gt).
+//   k_dlut_tc    dlut1^T[d, k] = sum_p gt[p, d] * dsim[p, k]: a 128-wide slice of the codebook width per CTA, all K
+//                codebook rows as accumulator columns, the pixel axis as the reduction, split over the CTAs; partial
+//                sums leave TMEM through red.global.add.f32.
+//
+// Both kernels: one persistent CTA per SM (256 threads) that owns the SM's tensor memory (512 columns); operands in
+// shared memory in the K-major no-swizzle canonical layout -- element (row r, k) at
+//     (r / 8) SBO + (k / 4) 128 + (r % 8) 16 + (k % 4) 4 bytes,   SBO = (KC / 4) 128 + 16
+// (recipe verified in profiles/micro/tc05_probe.cu; the 16 pad bytes make the transposing stores conflict-free) --
+// two stages, each a TF32 hi image and a lo image; a stage is refilled as soon as the MMAs that read it have
+// committed (mbarrier), so the tensor pipe always has the next chunk queued behind the running one.  Operands that
+// come from fp32 tensors pass through registers (split, 4x4 transposes where the source is contiguous along the
+// wrong axis); the codebook operand of k_sim_tc is pre-split once per call (k_build_wimg) and fetched with one bulk
+// async copy (cp.async.bulk + mbarrier complete_tx) per image.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc5 {
+
+constexpr int LBO = 128;                                    // bytes between the 16-byte K chunks of an 8-row group
+constexpr int THREADS = 256;
+__host__ __device__ constexpr int sbo_for(int kc) { return (kc / 4) * LBO + 16; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address
+    d |= (uint64_t)((LBO >> 4) & 0x3fff) << 16;             // leading byte offset
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;             // stride byte offset (8-row groups)
+    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (sm_100)
+    return d;                                               // SWIZZLE_NONE, base offset 0
+}
+__device__ __forceinline__ uint32_t instr_desc(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);   // F32 += TF32 x TF32, K-major
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n.reg .b64 t;\nmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one bulk asynchronous copy global -> shared (multiple of 16 bytes, 16-byte aligned both sides); completion is
+// signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// columns [c, c + cnt) of this warp's 32 TMEM lanes, cnt = 32 or 16 (warp-uniform)
+__device__ __forceinline__ void ld_cols(uint32_t taddr, int cnt, uint32_t (&v)[32])
+{
+    if (cnt >= 32) ld32(taddr, v); else ld16(taddr, v);
+    ld_wait();
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// TF32 hi / lo images of four consecutive reduction elements of one operand row
+__device__ __forceinline__ void store_split(uint32_t hi_base, uint32_t lo_base, uint32_t off, float a, float b, float c, float d, bool want_lo)
+{
+    const uint32_t ha = __float_as_uint(a) & 0xffffe000u, hb = __float_as_uint(b) & 0xffffe000u,
+                   hc = __float_as_uint(c) & 0xffffe000u, hd = __float_as_uint(d) & 0xffffe000u;
+    sts128u(hi_base + off, ha, hb, hc, hd);
+    if (want_lo)
+        sts128f(lo_base + off, a - __uint_as_float(ha), b - __uint_as_float(hb), c - __uint_as_float(hc), d - __uint_as_float(hd));
+}
+// four consecutive floats with the first `nvalid` inside the tensor (zeros behind); `vec` = 16-byte loads are legal
+__device__ __forceinline__ float4 ld4(const float* p, int nvalid, bool vec)
+{
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nvalid >= 4 && vec) {
+        v = __ldg(reinterpret_cast<const float4*>(p));
+    } else if (nvalid > 0) {
+        v.x = __ldg(p);
+        if (nvalid > 1) v.y = __ldg(p + 1);
+        if (nvalid > 2) v.z = __ldg(p + 2);
+        if (nvalid > 3) v.w = __ldg(p + 3);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A 128-row operand tile that comes from an fp32 tensor, one chunk of KC reduction elements at a time.
+//   TRANS = false: the source is contiguous along the reduction axis, element (r, k) = src[(row0 + r) ld + k0 + k].
+//                  A thread owns 16-byte pieces (row, four k); 8 consecutive lanes = 8 consecutive rows (conflict-free
+//                  stores), the lane's upper bits walk k: a warp instruction reads 64 contiguous bytes of 8 rows.
+//   TRANS = true:  the source is contiguous along the row axis, element (r, k) = src[(k0 + k) ld + row0 + r].
+//                  A thread owns a 4 x 4 block (rows 4 lane .. 4 lane + 3, four k = its warp's quad), loaded as four
+//                  16-byte vectors (coalesced: a warp reads 512 contiguous bytes per k) and transposed in registers.
+// Rows >= row_end and reduction elements >= k_end read as zeros.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KC, bool TRANS>
+struct RowTile {
+    static constexpr int Q = KC / 4;                        // 16-byte pieces per row
+    static constexpr int NREG = TRANS ? 4 : 2 * (Q / 4);    // float4 registers per thread
+    float4 v[NREG];
+
+    __device__ __forceinline__ void load(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
+                                         int64_t k0, int64_t k_end, bool vec, int tid)
+    {
+        const int lane = tid & 31, w = tid >> 5;
+        if (TRANS) {
+            const int k4 = w;                               // warps >= Q idle (KC = 16)
+            const int64_t r = row0 + 4 * lane;
+            const int nv = (int)min((int64_t)4, row_end - r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = k0 + 4 * k4 + j;
+                v[j] = (k4 < Q && k < k_end) ? ld4(src + k * ld + r, nv, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < NREG; ++it) {
+                const int u = it * 8 + w;
+                const int r = 8 * (u / (Q / 4)) + (lane & 7), k4 = 4 * (u % (Q / 4)) + (lane >> 3);
+                const int64_t k = k0 + 4 * k4;
+                v[it] = (row0 + r < row_end) ? ld4(src + (row0 + r) * ld + k, (int)min((int64_t)4, k_end - k), vec)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    // writes the hi (and lo) images of the loaded chunk; ss[] += squares per owned row (row_of() names them)
+    __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int sbo, bool want_lo, int tid, float (&ss)[4])
+    {
+        const int lane = tid & 31, w = tid >> 5;
+        if (TRANS) {
+            const int k4 = w;
+            if (k4 < Q) {
+                const float x[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
+                                       {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 4 * lane + i;
+                    store_split(hi_base, lo_base, (uint32_t)((r >> 3) * sbo + k4 * LBO + (r & 7) * 16), x[i][0], x[i][1], x[i][2], x[i][3], want_lo);
+                    ss[i] = fmaf(x[i][0], x[i][0], fmaf(x[i][1], x[i][1], fmaf(x[i][2], x[i][2], fmaf(x[i][3], x[i][3], ss[i]))));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < NREG; ++it) {
+                const int u = it * 8 + w;
+                const int r = 8 * (u / (Q / 4)) + (lane & 7), k4 = 4 * (u % (Q / 4)) + (lane >> 3);
+                store_split(hi_base, lo_base, (uint32_t)((r >> 3) * sbo + k4 * LBO + (r & 7) * 16), v[it].x, v[it].y, v[it].z, v[it].w, want_lo);
+                ss[it] = fmaf(v[it].x, v[it].x, fmaf(v[it].y, v[it].y, fmaf(v[it].z, v[it].z, fmaf(v[it].w, v[it].w, ss[it]))));
+            }
+        }
+    }
+    // the row that ss[i] of store() belongs to (-1: none)
+    static __device__ __forceinline__ int row_of(int i, int tid)
+    {
+        const int lane = tid & 31, w = tid >> 5;
+        if (TRANS) return w < Q ? 4 * lane + i : -1;
+        return i < NREG ? 8 * ((i * 8 + w) / (Q / 4)) + (lane & 7) : -1;
+    }
+};
+
+// The MMAs of one chunk: D[128 x (N0 | N1)] (+)= A[128 x KC] B[(N0 | N1) x KC]^T, `nterms` = 3: A_lo B_hi + A_hi B_lo +
+// A_hi B_hi, 1: A_hi B_hi only.  `fresh` overwrites the accumulators (first chunk of a tile).
+template <int KC>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            int sbo, int N0, int N1, int nterms, bool fresh)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int nn = half == 0 ? N0 : N1;
+        if (nn == 0) continue;
+        const uint32_t idesc = instr_desc(128, nn);
+        const uint32_t row0 = half == 0 ? 0u : (uint32_t)((N0 / 8) * sbo);
+        const uint32_t d = tmem + (half == 0 ? 0u : (uint32_t)N0);
+        uint32_t acc = fresh ? 0u : 1u;
+        for (int term = 3 - nterms; term < 3; ++term) {
+            const uint32_t a = term == 0 ? a_lo : a_hi, b = (term == 1 ? b_lo : b_hi) + row0;
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+                mma_tf32(d, smem_desc(a + ks * 2 * LBO, sbo), smem_desc(b + ks * 2 * LBO, sbo), idesc, acc);
+                acc = 1u;
+            }
+        }
+    }
+}
+
+struct SimStats {                       // double accumulators of the similarity-side loss terms (+ min, ordered-int key)
+    double simval, ent, rec;
+    int min_simval_key;
+    int pad;
+};
+__device__ __forceinline__ int float_key_tc(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_sim_tc: see the file header.  Per tile of 128 pixels:
+//   chunks c = 0 .. nchunks-1 of the codebook width: [wait for the MMAs that read this stage] -> thread 0 starts the
+//   bulk copies of the codebook images, all threads write the gt chunk (hi / lo, summing squares) and load the next
+//   one into registers -> block barrier -> thread 0 waits for the bulk copies, issues the chunk's MMAs, commits.
+//   epilogue: thread (row = t & 127, part = t >> 7) owns pixel `row` and the column range of its part; three passes
+//   over its accumulator columns (tcgen05.ld, 32 at a time): max / arg-max -> exp sums -> gradient, label bits.
+// Outputs: dsimT[tile][k][128] = d loss / d sim * (1 / |gt|) (zeros for padded rows / pixels), lmask[k / 32][pixel] =
+// label bits (sim == row max), and the loss partial sums.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KC, bool PLANAR>
+__global__ void __launch_bounds__(THREADS, 1)
+k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_anneal, const float* __restrict__ gt,
+         const uint8_t* __restrict__ wimg, const int* __restrict__ zarg, float* __restrict__ dsimT,
+         uint32_t* __restrict__ lmask, int64_t Npad, SimStats* __restrict__ stats)
+{
+    constexpr int SBO = sbo_for(KC);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int wbytes = (NP / 8) * SBO;                      // one codebook image (hi or lo) of one chunk
+    constexpr int xbytes = 16 * SBO;                        // one gt image
+    uint8_t* sW = smem_raw;                                 // [stage][hi, lo][wbytes]
+    uint8_t* sX = sW + 4 * (size_t)wbytes;                  // [stage][hi, lo][xbytes]
+    __shared__ __align__(8) uint64_t s_wfull[2], s_mma[2], s_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_ss[128];
+    __shared__ float s_pv[2][128], s_ps[2][128], s_pw[2][128];
+    __shared__ int s_pi[2][128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
+    const bool want_lo = nterms == 3;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_mma[s], 1); }
+        mbar_init(&s_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid < 128) s_ss[tid] = 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+
+    const int64_t n_tiles = (N + 127) / 128;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(gt) & 15) == 0) && (((PLANAR ? N : (int64_t)D) & 3) == 0);
+    const float invN = 1.0f / (float)N, ce = 0.3f * t_anneal * invN;
+    double l_sim = 0.0, l_ent = 0.0, l_rec = 0.0;
+    float l_min = INFINITY;
+
+    RowTile<KC, PLANAR> xt;
+    auto load_x = [&](int64_t tile, int c) {
+        // rows = pixels, reduction = codebook width
+        xt.load(gt, PLANAR ? N : (int64_t)D, tile * 128, N, (int64_t)c * KC, D, vec, tid);
+    };
+    if (my_tiles > 0) load_x(blockIdx.x, 0);
+
+    uint32_t g = 0;                                         // chunks staged so far by this CTA
+    int64_t tile = blockIdx.x;
+    for (int64_t it = 0; it < my_tiles; ++it, tile += gridDim.x) {
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < nchunks; ++c, ++g) {
+            const int s = (int)(g & 1);
+            const uint32_t u = g >> 1;
+            if (g >= 2) wait(smem_u32(&s_mma[s]), (u - 1) & 1);     // the MMAs that read this stage have completed
+            const uint32_t w_hi = smem_u32(sW) + (uint32_t)(2 * s) * wbytes, w_lo = w_hi + wbytes;
+            const uint32_t x_hi = smem_u32(sX) + (uint32_t)(2 * s) * xbytes, x_lo = x_hi + xbytes;
+            if (tid == 0) {
+                const uint32_t bar = smem_u32(&s_wfull[s]);
+                mbar_expect_tx(bar, (uint32_t)(want_lo ? 2 * wbytes : wbytes));
+                const uint8_t* src = wimg + (size_t)c * 2 * wbytes;
+                bulk_g2s(w_hi, src, (uint32_t)wbytes, bar);
+                if (want_lo) bulk_g2s(w_lo, src + wbytes, (uint32_t)wbytes, bar);
+            }
+            xt.store(x_hi, x_lo, SBO, want_lo, tid, ss);
+            if (c + 1 < nchunks) load_x(tile, c + 1);
+            else if (it + 1 < my_tiles) load_x(tile + gridDim.x, 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+            __syncthreads();
+            if (tid == 0) {
+                wait(smem_u32(&s_wfull[s]), u & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                issue_chunk<KC>(tmem, x_hi, x_lo, w_hi, w_lo, SBO, N0, N1, nterms, c == 0);
+                commit(smem_u32(&s_mma[s]));
+                if (c == nchunks - 1) commit(smem_u32(&s_acc));
+            }
+        }
+        // ---- 1 / |gt| of the tile's pixels
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = RowTile<KC, PLANAR>::row_of(i, tid);
+            if (r >= 0) atomicAdd(&s_ss[r], ss[i]);
+        }
+        __syncthreads();
+        const int row = tid & 127, part = tid >> 7;
+        const int64_t n = tile * 128 + row;
+        const bool rv = n < N;
+        const float inv = rv ? 1.f / sqrtf(s_ss[row]) : 0.f;
+        const int za = rv ? __ldg(zarg + n) : -1;
+        wait(smem_u32(&s_acc), (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+
+        // ---- epilogue: the similarity row of pixel `row`, columns [cbeg, cend)
+        const int C0 = min(NP, 32 * ((NP + 63) / 64));
+        const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        uint32_t v[32];
+        float bv = -INFINITY;
+        int bi = 0;
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            const int cnt = min(32, cend - c0);
+            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float sv = __uint_as_float(v[j]) * inv;
+                if (j < cnt && c0 + j < K && sv > bv) { bv = sv; bi = c0 + j; }     // ascending columns, strict >: first maximum
+            }
+        }
+        s_pv[part][row] = bv;
+        s_pi[part][row] = bi;
+        __syncthreads();
+        const float v0 = s_pv[0][row], v1 = s_pv[1][row];
+        const float smax = v1 > v0 ? v1 : v0;
+        const int sarg = v1 > v0 ? s_pi[1][row] : s_pi[0][row];
+        float asum = 0.f, wsum = 0.f;
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            const int cnt = min(32, cend - c0);
+            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float a = t_anneal * (__uint_as_float(v[j]) * inv - smax);
+                const float pa = __expf(a);
+                if (j < cnt && c0 + j < K) { asum += pa; wsum = fmaf(pa, a, wsum); }
+            }
+        }
+        s_ps[part][row] = asum;
+        s_pw[part][row] = wsum;
+        __syncthreads();
+        asum = s_ps[0][row] + s_ps[1][row];
+        wsum = s_pw[0][row] + s_pw[1][row];
+        const float ainv = 1.f / asum, logZ = __logf(asum);
+        const float E = wsum * ainv - logZ;                 // sum P log P,  P = softmax(t sim)
+        float rec = 0.f;
+        float* const out = dsimT + (size_t)tile * NP * 128 + row;
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            const int cnt = min(32, cend - c0);
+            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < cnt) {
+                    const int k = c0 + j;
+                    const float sv = __uint_as_float(v[j]) * inv;
+                    const float a = t_anneal * (sv - smax);
+                    const float P = __expf(a) * ainv;
+                    float ds = -ce * P * ((a - logZ) - E);
+                    ds -= (k == sarg) ? invN : 0.f;
+                    ds -= (k == za) ? invN : 0.f;
+                    rec = (k == za) ? sv : rec;
+                    const bool real = k < K;
+                    bits |= (real && sv == smax) ? (1u << j) : 0u;
+                    out[(size_t)k * 128] = real ? ds * inv : 0.f;
+                }
+            }
+            lmask[(size_t)(c0 >> 5) * Npad + (size_t)n] = bits;
+        }
+        if (rv) {
+            l_rec += (double)rec;
+            if (part == 0) { l_sim += (double)smax; l_ent += (double)E; l_min = fminf(l_min, smax); }
+        }
+        if (tid < 128) s_ss[tid] = 0.f;
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();                                    // TMEM, s_ss and the exchange arrays are free for the next tile
+    }
+
+    // ---- loss partial sums
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        l_sim += __shfl_xor_sync(0xffffffffu, l_sim, o);
+        l_ent += __shfl_xor_sync(0xffffffffu, l_ent, o);
+        l_rec += __shfl_xor_sync(0xffffffffu, l_rec, o);
+        l_min = fminf(l_min, __shfl_xor_sync(0xffffffffu, l_min, o));
+    }
+    if (lane == 0 && my_tiles > 0) {
+        atomicAdd(&stats->simval, l_sim);
+        atomicAdd(&stats->ent, l_ent);
+        atomicAdd(&stats->rec, l_rec);
+        if (l_min < INFINITY) atomicMin(&stats->min_simval_key, float_key_tc(l_min));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_dlut_tc: dlut1[k, d0 + r] += sum over this CTA's pixels of dsim[p, k] gt[p, d0 + r].  CTA = (slice of 128 codebook-
+// width columns, every n_ranges-th pixel tile).  A operand = the gt slice (rows = d, reduction = pixels), B operand =
+// dsimT (rows = codebook rows, reduction = pixels), accumulators [128 x NP] fp32 in TMEM for the whole kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KC, bool PLANAR>
+__global__ void __launch_bounds__(THREADS, 1)
+k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float* __restrict__ gt,
+          const float* __restrict__ dsimT, float* __restrict__ dlut1)
+{
+    constexpr int SBO = sbo_for(KC);
+    constexpr int Q = KC / 4;
+    constexpr int CPT = 128 / KC;                           // chunks per pixel tile
+    constexpr int BIT = KC == 32 ? 10 : 8;                  // B-operand pieces per thread: ceil((NP / 8)(Q / 4) / 8), NP <= 304 | 512
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int bbytes = (NP / 8) * SBO;
+    constexpr int abytes = 16 * SBO;
+    uint8_t* sB = smem_raw;                                 // [stage][hi, lo][bbytes]
+    uint8_t* sA = sB + 4 * (size_t)bbytes;                  // [stage][hi, lo][abytes]
+    __shared__ __align__(8) uint64_t s_mma[2], s_acc;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
+    const bool want_lo = nterms == 3;
+    const int slice = blockIdx.x % n_slices, range = blockIdx.x / n_slices, n_ranges = gridDim.x / n_slices;
+    const int64_t d0 = (int64_t)slice * 128;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) mbar_init(&s_mma[s], 1);
+        mbar_init(&s_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+
+    const int64_t n_tiles = (N + 127) / 128;
+    const int64_t my_tiles = range < n_tiles ? (n_tiles - range + n_ranges - 1) / n_ranges : 0;
+    const int64_t my_chunks = my_tiles * CPT;
+    const bool vec = ((reinterpret_cast<uintptr_t>(gt) & 15) == 0) && (((PLANAR ? N : (int64_t)D) & 3) == 0);
+    const int b_units = (NP / 8) * (Q / 4);
+
+    // PLANAR: gt[d][pixel] is contiguous along the reduction (pixels) -> direct; row-major gt[pixel][d] -> transposed
+    RowTile<KC, !PLANAR> at;
+    float4 bv[BIT];
+    auto load_ab = [&](int64_t ch) {
+        const int64_t tile = range + (ch / CPT) * n_ranges;
+        const int64_t p0 = tile * 128 + (ch % CPT) * KC;
+        at.load(gt, PLANAR ? N : (int64_t)D, d0, D, p0, N, vec, tid);
+        const float* bsrc = dsimT + (size_t)tile * NP * 128 + (ch % CPT) * KC;
+#pragma unroll
+        for (int i = 0; i < BIT; ++i) {
+            const int u = i * 8 + warp;
+            const int r = 8 * (u / (Q / 4)) + (lane & 7), k4 = 4 * (u % (Q / 4)) + (lane >> 3);
+            if (u < b_units) bv[i] = __ldg(reinterpret_cast<const float4*>(bsrc + (size_t)r * 128 + 4 * k4));
+        }
+    };
+    if (my_chunks > 0) load_ab(0);
+
+    float ss_unused[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t ch = 0; ch < my_chunks; ++ch) {
+        const int s = (int)(ch & 1);
+        const uint32_t u = (uint32_t)(ch >> 1);
+        if (ch >= 2) wait(smem_u32(&s_mma[s]), (u - 1) & 1);
+        const uint32_t b_hi = smem_u32(sB) + (uint32_t)(2 * s) * bbytes, b_lo = b_hi + bbytes;
+        const uint32_t a_hi = smem_u32(sA) + (uint32_t)(2 * s) * abytes, a_lo = a_hi + abytes;
+        at.store(a_hi, a_lo, SBO, want_lo, tid, ss_unused);
+#pragma unroll
+        for (int i = 0; i < BIT; ++i) {
+            const int uu = i * 8 + warp;
+            const int r = 8 * (uu / (Q / 4)) + (lane & 7), k4 = 4 * (uu % (Q / 4)) + (lane >> 3);
+            if (uu < b_units)
+                store_split(b_hi, b_lo, (uint32_t)((r >> 3) * SBO + k4 * LBO + (r & 7) * 16), bv[i].x, bv[i].y, bv[i].z, bv[i].w, want_lo);
+        }
+        if (ch + 1 < my_chunks) load_ab(ch + 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            issue_chunk<KC>(tmem, a_hi, a_lo, b_hi, b_lo, SBO, N0, N1, nterms, ch == 0);
+            commit(smem_u32(&s_mma[s]));
+            if (ch == my_chunks - 1) commit(smem_u32(&s_acc));
+        }
+    }
+
+    if (my_chunks > 0) {
+        wait(smem_u32(&s_acc), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int row = tid & 127, part = tid >> 7;
+        const int C0 = min(NP, 32 * ((NP + 63) / 64));
+        const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        const bool dv = d0 + row < D;
+        float* const out = dlut1 + d0 + row;
+        uint32_t v[32];
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            const int cnt = min(32, cend - c0);
+            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < cnt && c0 + j < K && dv) atomicAdd(out + (size_t)(c0 + j) * D, __uint_as_float(v[j]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// The codebook operand of k_sim_tc: lut1 split once into TF32 hi / lo images, chunk by chunk, already in the shared-
+// memory layout (rows >= K and columns >= D are zeros) so that a stage is one bulk copy per image.
+__global__ void __launch_bounds__(256) k_build_wimg(int K, int D, int NP, int KC, int nchunks, int sbo,
+                                                    const float* __restrict__ lut1, uint8_t* __restrict__ img)
+{
+    const int wbytes = (NP / 8) * sbo;
+    const int total = nchunks * NP * KC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i / (NP * KC), rk = i % (NP * KC), r = rk / KC, k = rk % KC;
+        const int d = c * KC + k;
+        const float v = (r < K && d < D) ? lut1[(size_t)r * D + d] : 0.f;
+        const uint32_t hi = __float_as_uint(v) & 0xffffe000u;
+        const size_t off = (size_t)c * 2 * wbytes + (size_t)((r >> 3) * sbo + (k >> 2) * LBO + (r & 7) * 16 + (k & 3) * 4);
+        *reinterpret_cast<uint32_t*>(img + off) = hi;
+        *reinterpret_cast<float*>(img + off + wbytes) = v - __uint_as_float(hi);
+    }
+}
+
+}  // namespace tc5
