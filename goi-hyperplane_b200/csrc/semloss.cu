@@ -391,7 +391,6 @@ __global__ void k_semloss_finalize(int64_t N, int K, const Accum* acc, float* lo
 struct Geometry {
     int NP;            // codebook rows padded to 16 accumulator columns
     int KC;            // reduction elements per staged chunk: 32, or 16 when the codebook is longer than 304 rows
-    int sbo;           // bytes between 8-row groups of an operand image
     int nchunks;       // chunks of the codebook width (k_sim_tc)
     int wbytes;        // one codebook image of one chunk
     int KW;            // label words per pixel
@@ -403,13 +402,12 @@ Geometry geometry(int64_t N, int K, int D)
     Geometry g{};
     g.NP = ((K + 15) / 16) * 16;
     g.KC = g.NP <= 304 ? 32 : 16;
-    g.sbo = tc5::sbo_for(g.KC);
     g.nchunks = (D + g.KC - 1) / g.KC;
-    g.wbytes = (g.NP / 8) * g.sbo;
+    g.wbytes = g.NP * tc5::row_bytes(g.KC);
     g.KW = (g.NP + 31) / 32;
     g.ntiles = (N + 127) / 128;
     g.Npad = g.ntiles * 128;
-    g.smem = (size_t)4 * g.wbytes + (size_t)4 * 16 * g.sbo;
+    g.smem = (size_t)4 * g.wbytes + (size_t)4 * 128 * tc5::row_bytes(g.KC) + 1024;   // + alignment slack
     return g;
 }
 
@@ -568,7 +566,7 @@ int goi_semantic_loss(const goi_semloss_args* a, void* stream)
 
     k_semloss_init<<<1, 1, 0, st>>>(w.acc);
     k_lut_normalize<<<K, 128, 0, st>>>(K, D, a->lut, w.lut1, w.lut_norm);
-    tc5::k_build_wimg<<<148, 256, 0, st>>>(K, D, g.NP, g.KC, g.nchunks, g.sbo, w.lut1, w.wimg);
+    tc5::k_build_wimg<<<148, 256, 0, st>>>(K, D, g.NP, g.KC, g.nchunks, w.lut1, w.wimg);
     SL_CUDA(cudaGetLastError(), "prologue kernels");
     if (a->dL_dmlp_weight) SL_CUDA(cudaMemsetAsync(a->dL_dmlp_weight, 0, sizeof(float) * (size_t)K * a->S, st), "zero dW");
     if (a->dL_dmlp_bias) SL_CUDA(cudaMemsetAsync(a->dL_dmlp_bias, 0, sizeof(float) * (size_t)K, st), "zero db");

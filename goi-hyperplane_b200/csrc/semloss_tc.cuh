@@ -12,9 +12,11 @@
 //                sums leave TMEM through red.global.add.f32.
 //
 // Both kernels: one persistent CTA per SM (256 threads) that owns the SM's tensor memory (512 columns); operands in
-// shared memory in the K-major no-swizzle canonical layout -- element (row r, k) at
-//     (r / 8) SBO + (k / 4) 128 + (r % 8) 16 + (k % 4) 4 bytes,   SBO = (KC / 4) 128 + 16
-// (recipe verified in profiles/micro/tc05_probe.cu; the 16 pad bytes make the transposing stores conflict-free) --
+// shared memory in the K-major SWIZZLED canonical layout -- a row is one chunk of KC reduction elements (128 B with
+// SWIZZLE_128B at KC = 32, 64 B with SWIZZLE_64B at KC = 16), rows are contiguous, and the 16-byte piece c of row r
+// sits at piece c ^ x(r), x(r) = r % 8 | (r / 2) % 4 (recipe verified in profiles/micro/tc05_probe_sw.cu).  The XOR is
+// what lets a warp read 128 contiguous bytes of a source row AND store them without bank conflicts: with the
+// unswizzled layout the loads had to be spread over 8 rows per instruction, which saturated the L1 data pipe --
 // two stages, each a TF32 hi image and a lo image; a stage is refilled as soon as the MMAs that read it have
 // committed (mbarrier), so the tensor pipe always has the next chunk queued behind the running one.  Operands that
 // come from fp32 tensors pass through registers (split, 4x4 transposes where the source is contiguous along the
@@ -26,19 +28,23 @@
 
 namespace tc5 {
 
-constexpr int LBO = 128;                                    // bytes between the 16-byte K chunks of an 8-row group
 constexpr int THREADS = 256;
-__host__ __device__ constexpr int sbo_for(int kc) { return (kc / 4) * LBO + 16; }
+__host__ __device__ constexpr int row_bytes(int kc) { return 4 * kc; }                      // one operand row of one chunk
+__host__ __device__ constexpr int swz(int kc, int r) { return kc == 32 ? (r & 7) : ((r >> 1) & 3); }
+// byte offset of the 16-byte piece c (reduction elements 4c .. 4c+3) of row r inside an operand image
+__host__ __device__ constexpr int piece_off(int kc, int r, int c) { return r * row_bytes(kc) + ((c ^ swz(kc, r)) << 4); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int sbo)
+template <int KC>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
 {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address
-    d |= (uint64_t)((LBO >> 4) & 0x3fff) << 16;             // leading byte offset
-    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;             // stride byte offset (8-row groups)
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address (image bases are 1024-byte aligned)
+    d |= (uint64_t)1 << 16;                                 // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(((8 * row_bytes(KC)) >> 4) & 0x3fff) << 32;   // stride byte offset: 8-row groups are contiguous
     d |= (uint64_t)1 << 46;                                 // descriptor version 1 (sm_100)
-    return d;                                               // SWIZZLE_NONE, base offset 0
+    d |= (uint64_t)(KC == 32 ? 2 : 4) << 61;                // SWIZZLE_128B | SWIZZLE_64B
+    return d;
 }
 __device__ __forceinline__ uint32_t instr_desc(int m, int n)
 {
@@ -93,6 +99,37 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, int cnt, uint32_t (&v)[3
     if (cnt >= 32) ld32(taddr, v); else ld16(taddr, v);
     ld_wait();
 }
+// without the wait: the caller overlaps the load with arithmetic on the previous block
+__device__ __forceinline__ void ld_cols_nowait(uint32_t taddr, int cnt, uint32_t (&v)[32])
+{
+    if (cnt >= 32) ld32(taddr, v); else ld16(taddr, v);
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Calls f(v, c0, cnt, full) for the 32-column blocks of [cbeg, cend) (the last one may be 16 wide), with the TMEM load
+// of block b + 1 in flight while block b is processed.  full = every column of the block is a real codebook row.
+template <typename F>
+__device__ __forceinline__ void for_blocks(uint32_t lane_base, int cbeg, int cend, int K, F&& f)
+{
+    uint32_t va[32], vb[32];
+    if (cbeg >= cend) return;
+    ld_cols_nowait(lane_base + (uint32_t)cbeg, min(32, cend - cbeg), va);
+    for (int c0 = cbeg; c0 < cend; c0 += 64) {
+        const int c1 = c0 + 32, c2 = c0 + 64;
+        ld_wait();
+        if (c1 < cend) ld_cols_nowait(lane_base + (uint32_t)c1, min(32, cend - c1), vb);
+        f(va, c0, min(32, cend - c0), c0 + 32 <= K);
+        if (c1 < cend) {
+            ld_wait();
+            if (c2 < cend) ld_cols_nowait(lane_base + (uint32_t)c2, min(32, cend - c2), va);
+            f(vb, c1, min(32, cend - c1), c1 + 32 <= K);
+        }
+    }
+}
 __device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -138,16 +175,22 @@ __device__ __forceinline__ float4 ld4(const float* p, int nvalid, bool vec)
 template <int KC, bool TRANS>
 struct RowTile {
     static constexpr int Q = KC / 4;                        // 16-byte pieces per row
-    static constexpr int NREG = TRANS ? 4 : 2 * (Q / 4);    // float4 registers per thread
+    static constexpr int RPU = 32 / Q;                      // rows per warp instruction (direct mode)
+    static constexpr int NREG = TRANS ? 4 : Q / 2;          // float4 registers per thread
     float4 v[NREG];
+
+    // transposed mode: lane = hi * 8 + k4l * 2 + lo -> row quad 8 (warp % 4) + 2 hi + lo, piece 4 (warp / 4) + k4l.
+    // A store phase (8 consecutive lanes) then holds 4 pieces x 2 row parities = 8 different swizzled positions, and a
+    // load instruction reads 4 source rows x 128 contiguous bytes.
+    static __device__ __forceinline__ int t_r4(int tid) { const int lane = tid & 31; return 8 * ((tid >> 5) & 3) + 2 * (lane >> 3) + (lane & 1); }
+    static __device__ __forceinline__ int t_k4(int tid) { return 4 * (tid >> 7) + ((tid >> 1) & 3); }
 
     __device__ __forceinline__ void load(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
                                          int64_t k0, int64_t k_end, bool vec, int tid)
     {
-        const int lane = tid & 31, w = tid >> 5;
         if (TRANS) {
-            const int k4 = w;                               // warps >= Q idle (KC = 16)
-            const int64_t r = row0 + 4 * lane;
+            const int k4 = t_k4(tid);                       // warps >= 4 idle at KC = 16
+            const int64_t r = row0 + 4 * t_r4(tid);
             const int nv = (int)min((int64_t)4, row_end - r);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -155,38 +198,36 @@ struct RowTile {
                 v[j] = (k4 < Q && k < k_end) ? ld4(src + k * ld + r, nv, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
+            const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
             for (int it = 0; it < NREG; ++it) {
-                const int u = it * 8 + w;
-                const int r = 8 * (u / (Q / 4)) + (lane & 7), k4 = 4 * (u % (Q / 4)) + (lane >> 3);
-                const int64_t k = k0 + 4 * k4;
+                const int r = (it * 8 + w) * RPU + lane / Q, c = lane % Q;
+                const int64_t k = k0 + 4 * c;
                 v[it] = (row0 + r < row_end) ? ld4(src + (row0 + r) * ld + k, (int)min((int64_t)4, k_end - k), vec)
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
     // writes the hi (and lo) images of the loaded chunk; ss[] += squares per owned row (row_of() names them)
-    __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int sbo, bool want_lo, int tid, float (&ss)[4])
+    __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, bool want_lo, int tid, float (&ss)[4])
     {
-        const int lane = tid & 31, w = tid >> 5;
         if (TRANS) {
-            const int k4 = w;
+            const int k4 = t_k4(tid), r4 = t_r4(tid);
             if (k4 < Q) {
                 const float x[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
                                        {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int r = 4 * lane + i;
-                    store_split(hi_base, lo_base, (uint32_t)((r >> 3) * sbo + k4 * LBO + (r & 7) * 16), x[i][0], x[i][1], x[i][2], x[i][3], want_lo);
+                    store_split(hi_base, lo_base, (uint32_t)piece_off(KC, 4 * r4 + i, k4), x[i][0], x[i][1], x[i][2], x[i][3], want_lo);
                     ss[i] = fmaf(x[i][0], x[i][0], fmaf(x[i][1], x[i][1], fmaf(x[i][2], x[i][2], fmaf(x[i][3], x[i][3], ss[i]))));
                 }
             }
         } else {
+            const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
             for (int it = 0; it < NREG; ++it) {
-                const int u = it * 8 + w;
-                const int r = 8 * (u / (Q / 4)) + (lane & 7), k4 = 4 * (u % (Q / 4)) + (lane >> 3);
-                store_split(hi_base, lo_base, (uint32_t)((r >> 3) * sbo + k4 * LBO + (r & 7) * 16), v[it].x, v[it].y, v[it].z, v[it].w, want_lo);
+                const int r = (it * 8 + w) * RPU + lane / Q, c = lane % Q;
+                store_split(hi_base, lo_base, (uint32_t)piece_off(KC, r, c), v[it].x, v[it].y, v[it].z, v[it].w, want_lo);
                 ss[it] = fmaf(v[it].x, v[it].x, fmaf(v[it].y, v[it].y, fmaf(v[it].z, v[it].z, fmaf(v[it].w, v[it].w, ss[it]))));
             }
         }
@@ -194,9 +235,8 @@ struct RowTile {
     // the row that ss[i] of store() belongs to (-1: none)
     static __device__ __forceinline__ int row_of(int i, int tid)
     {
-        const int lane = tid & 31, w = tid >> 5;
-        if (TRANS) return w < Q ? 4 * lane + i : -1;
-        return i < NREG ? 8 * ((i * 8 + w) / (Q / 4)) + (lane & 7) : -1;
+        if (TRANS) return t_k4(tid) < Q ? 4 * t_r4(tid) + i : -1;
+        return i < NREG ? (i * 8 + (tid >> 5)) * RPU + (tid & 31) / Q : -1;
     }
 };
 
@@ -204,21 +244,21 @@ struct RowTile {
 // A_hi B_hi, 1: A_hi B_hi only.  `fresh` overwrites the accumulators (first chunk of a tile).
 template <int KC>
 __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            int sbo, int N0, int N1, int nterms, bool fresh)
+                                            int N0, int N1, int nterms, bool fresh)
 {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int nn = half == 0 ? N0 : N1;
         if (nn == 0) continue;
         const uint32_t idesc = instr_desc(128, nn);
-        const uint32_t row0 = half == 0 ? 0u : (uint32_t)((N0 / 8) * sbo);
+        const uint32_t row0 = half == 0 ? 0u : (uint32_t)(N0 * row_bytes(KC));
         const uint32_t d = tmem + (half == 0 ? 0u : (uint32_t)N0);
         uint32_t acc = fresh ? 0u : 1u;
         for (int term = 3 - nterms; term < 3; ++term) {
             const uint32_t a = term == 0 ? a_lo : a_hi, b = (term == 1 ? b_lo : b_hi) + row0;
 #pragma unroll
             for (int ks = 0; ks < KC / 8; ++ks) {
-                mma_tf32(d, smem_desc(a + ks * 2 * LBO, sbo), smem_desc(b + ks * 2 * LBO, sbo), idesc, acc);
+                mma_tf32(d, smem_desc<KC>(a + ks * 32), smem_desc<KC>(b + ks * 32), idesc, acc);   // a k-step = 8 elements = 32 bytes into the row
                 acc = 1u;
             }
         }
@@ -248,10 +288,10 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
          const uint8_t* __restrict__ wimg, const int* __restrict__ zarg, float* __restrict__ dsimT,
          uint32_t* __restrict__ lmask, int64_t Npad, SimStats* __restrict__ stats)
 {
-    constexpr int SBO = sbo_for(KC);
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int wbytes = (NP / 8) * SBO;                      // one codebook image (hi or lo) of one chunk
-    constexpr int xbytes = 16 * SBO;                        // one gt image
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned
+    const int wbytes = NP * row_bytes(KC);                  // one codebook image (hi or lo) of one chunk
+    constexpr int xbytes = 128 * row_bytes(KC);             // one gt image
     uint8_t* sW = smem_raw;                                 // [stage][hi, lo][wbytes]
     uint8_t* sX = sW + 4 * (size_t)wbytes;                  // [stage][hi, lo][xbytes]
     __shared__ __align__(8) uint64_t s_wfull[2], s_mma[2], s_acc;
@@ -285,12 +325,17 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
     double l_sim = 0.0, l_ent = 0.0, l_rec = 0.0;
     float l_min = INFINITY;
 
-    RowTile<KC, PLANAR> xt;
-    auto load_x = [&](int64_t tile, int c) {
-        // rows = pixels, reduction = codebook width
-        xt.load(gt, PLANAR ? N : (int64_t)D, tile * 128, N, (int64_t)c * KC, D, vec, tid);
+    // Two register sets: the loads of chunk g + 2 go out right after chunk g has been written to shared memory, so a
+    // load has a whole chunk period to land before it is consumed.
+    RowTile<KC, PLANAR> xa, xb;
+    auto load_x = [&](RowTile<KC, PLANAR>& xt, int64_t it2, int c2) {
+        // rows = pixels, reduction = codebook width; (it2, c2) may run past this tile: normalise
+        it2 += c2 / nchunks;
+        c2 %= nchunks;
+        if (it2 < my_tiles) xt.load(gt, PLANAR ? N : (int64_t)D, (blockIdx.x + it2 * gridDim.x) * 128, N, (int64_t)c2 * KC, D, vec, tid);
     };
-    if (my_tiles > 0) load_x(blockIdx.x, 0);
+    load_x(xa, 0, 0);
+    load_x(xb, 0, 1);
 
     uint32_t g = 0;                                         // chunks staged so far by this CTA
     int64_t tile = blockIdx.x;
@@ -309,15 +354,15 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
                 bulk_g2s(w_hi, src, (uint32_t)wbytes, bar);
                 if (want_lo) bulk_g2s(w_lo, src + wbytes, (uint32_t)wbytes, bar);
             }
-            xt.store(x_hi, x_lo, SBO, want_lo, tid, ss);
-            if (c + 1 < nchunks) load_x(tile, c + 1);
-            else if (it + 1 < my_tiles) load_x(tile + gridDim.x, 0);
+            if (s == 0) xa.store(x_hi, x_lo, want_lo, tid, ss); else xb.store(x_hi, x_lo, want_lo, tid, ss);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
             __syncthreads();
+            // behind the fence (a fence in front of the loads would wait for them to land)
+            if (s == 0) load_x(xa, it, c + 2); else load_x(xb, it, c + 2);
             if (tid == 0) {
                 wait(smem_u32(&s_wfull[s]), u & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                issue_chunk<KC>(tmem, x_hi, x_lo, w_hi, w_lo, SBO, N0, N1, nterms, c == 0);
+                issue_chunk<KC>(tmem, x_hi, x_lo, w_hi, w_lo, N0, N1, nterms, c == 0);
                 commit(smem_u32(&s_mma[s]));
                 if (c == nchunks - 1) commit(smem_u32(&s_acc));
             }
@@ -337,70 +382,103 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
         wait(smem_u32(&s_acc), (uint32_t)(it & 1));
         asm volatile("tcgen05.fence::after_thread_sync;");
 
-        // ---- epilogue: the similarity row of pixel `row`, columns [cbeg, cend)
+        // ---- epilogue: the similarity row of pixel `row`, columns [cbeg, cend).  Everything is evaluated on the raw
+        // accumulators r_k (sim_k = r_k / |gt|, a positive scale): a2_k = c2 (r_k - r_max) = log2(e) t (sim_k - sim_max).
         const int C0 = min(NP, 32 * ((NP + 63) / 64));
         const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
         const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        uint32_t v[32];
-        float bv = -INFINITY;
-        int bi = 0;
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-            const int cnt = min(32, cend - c0);
-            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+        constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+        // pass 1: row maximum, its first index, and the accumulator of column k^ (two chains: even / odd columns)
+        float bv0 = -INFINITY, bv1 = -INFINITY, rec_raw = 0.f;
+        int bi0 = 0, bi1 = 0;
+        for_blocks(lane_base, cbeg, cend, K, [&](const uint32_t (&v)[32], int c0, int cnt, bool full) {
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float sv = __uint_as_float(v[j]) * inv;
-                if (j < cnt && c0 + j < K && sv > bv) { bv = sv; bi = c0 + j; }     // ascending columns, strict >: first maximum
+                for (int j = 0; j < 32; j += 2) {
+                    const float r0 = __uint_as_float(v[j]), r1 = __uint_as_float(v[j + 1]);
+                    if (r0 > bv0) { bv0 = r0; bi0 = c0 + j; }
+                    if (r1 > bv1) { bv1 = r1; bi1 = c0 + j + 1; }
+                    rec_raw = (c0 + j == za) ? r0 : rec_raw;
+                    rec_raw = (c0 + j + 1 == za) ? r1 : rec_raw;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float r = __uint_as_float(v[j]);
+                    if (j < cnt && c0 + j < K) {
+                        if (r > bv0) { bv0 = r; bi0 = c0 + j; }
+                        rec_raw = (c0 + j == za) ? r : rec_raw;
+                    }
+                }
             }
-        }
-        s_pv[part][row] = bv;
-        s_pi[part][row] = bi;
+        });
+        if (bv1 > bv0 || (bv1 == bv0 && bi1 < bi0)) { bv0 = bv1; bi0 = bi1; }     // first maximum
+        s_pv[part][row] = bv0;
+        s_pi[part][row] = bi0;
         __syncthreads();
         const float v0 = s_pv[0][row], v1 = s_pv[1][row];
-        const float smax = v1 > v0 ? v1 : v0;
+        const float rmax = v1 > v0 ? v1 : v0;
         const int sarg = v1 > v0 ? s_pi[1][row] : s_pi[0][row];
-        float asum = 0.f, wsum = 0.f;
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-            const int cnt = min(32, cend - c0);
-            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+        const float c2 = LOG2E * t_anneal * inv;
+        // pass 2: sum 2^a2 and sum 2^a2 a2
+        float asum0 = 0.f, asum1 = 0.f, wsum0 = 0.f, wsum1 = 0.f;
+        for_blocks(lane_base, cbeg, cend, K, [&](const uint32_t (&v)[32], int c0, int cnt, bool full) {
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float a = t_anneal * (__uint_as_float(v[j]) * inv - smax);
-                const float pa = __expf(a);
-                if (j < cnt && c0 + j < K) { asum += pa; wsum = fmaf(pa, a, wsum); }
+                for (int j = 0; j < 32; j += 2) {
+                    const float a0 = c2 * (__uint_as_float(v[j]) - rmax), a1 = c2 * (__uint_as_float(v[j + 1]) - rmax);
+                    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                    asum0 += p0; asum1 += p1;
+                    wsum0 = fmaf(p0, a0, wsum0); wsum1 = fmaf(p1, a1, wsum1);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a0 = c2 * (__uint_as_float(v[j]) - rmax);
+                    const float p0 = ex2_approx(a0);
+                    if (j < cnt && c0 + j < K) { asum0 += p0; wsum0 = fmaf(p0, a0, wsum0); }
+                }
             }
-        }
-        s_ps[part][row] = asum;
-        s_pw[part][row] = wsum;
+        });
+        s_ps[part][row] = asum0 + asum1;
+        s_pw[part][row] = wsum0 + wsum1;
         __syncthreads();
-        asum = s_ps[0][row] + s_ps[1][row];
-        wsum = s_pw[0][row] + s_pw[1][row];
+        const float asum = s_ps[0][row] + s_ps[1][row];
+        const float wsum = LN2 * (s_pw[0][row] + s_pw[1][row]);
         const float ainv = 1.f / asum, logZ = __logf(asum);
         const float E = wsum * ainv - logZ;                 // sum P log P,  P = softmax(t sim)
-        float rec = 0.f;
+        // pass 3: d loss / d sim_k * (1 / |gt|) = kd 2^a2 (ln2 a2 - (logZ + E)) (+ the two one-hot terms below), label bits
+        const float kd = -ce * ainv * inv, LE = logZ + E;
         float* const out = dsimT + (size_t)tile * NP * 128 + row;
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-            const int cnt = min(32, cend - c0);
-            ld_cols(lane_base + (uint32_t)c0, cnt, v);
+        for_blocks(lane_base, cbeg, cend, K, [&](const uint32_t (&v)[32], int c0, int cnt, bool full) {
             uint32_t bits = 0;
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < cnt) {
-                    const int k = c0 + j;
-                    const float sv = __uint_as_float(v[j]) * inv;
-                    const float a = t_anneal * (sv - smax);
-                    const float P = __expf(a) * ainv;
-                    float ds = -ce * P * ((a - logZ) - E);
-                    ds -= (k == sarg) ? invN : 0.f;
-                    ds -= (k == za) ? invN : 0.f;
-                    rec = (k == za) ? sv : rec;
-                    const bool real = k < K;
-                    bits |= (real && sv == smax) ? (1u << j) : 0u;
-                    out[(size_t)k * 128] = real ? ds * inv : 0.f;
+                for (int j = 0; j < 32; ++j) {
+                    const float r = __uint_as_float(v[j]);
+                    const float a2 = c2 * (r - rmax);
+                    out[(size_t)(c0 + j) * 128] = kd * ex2_approx(a2) * fmaf(a2, LN2, -LE);
+                    bits |= (r == rmax) ? (1u << j) : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < cnt) {
+                        const float r = __uint_as_float(v[j]);
+                        const float a2 = c2 * (r - rmax);
+                        const bool real = c0 + j < K;
+                        out[(size_t)(c0 + j) * 128] = real ? kd * ex2_approx(a2) * fmaf(a2, LN2, -LE) : 0.f;
+                        bits |= (real && r == rmax) ? (1u << j) : 0u;
+                    }
                 }
             }
             lmask[(size_t)(c0 >> 5) * Npad + (size_t)n] = bits;
-        }
+        });
+        // the one-hot terms -(1/N)([k = k*] + [k = k^]) land on the columns this thread wrote itself
+        const float oh = invN * inv;
+        if (sarg >= cbeg && sarg < cend) out[(size_t)sarg * 128] -= oh;
+        if (za >= cbeg && za < cend) out[(size_t)za * 128] -= oh;
+        const float smax = rmax * inv, rec = rec_raw * inv;
         if (rv) {
             l_rec += (double)rec;
             if (part == 0) { l_sim += (double)smax; l_ent += (double)E; l_min = fminf(l_min, smax); }
@@ -439,13 +517,13 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float* __restrict__ gt,
           const float* __restrict__ dsimT, float* __restrict__ dlut1)
 {
-    constexpr int SBO = sbo_for(KC);
-    constexpr int Q = KC / 4;
+    constexpr int Q = KC / 4, RPU = 32 / Q;                 // pieces per row; rows per warp instruction
     constexpr int CPT = 128 / KC;                           // chunks per pixel tile
-    constexpr int BIT = KC == 32 ? 10 : 8;                  // B-operand pieces per thread: ceil((NP / 8)(Q / 4) / 8), NP <= 304 | 512
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int bbytes = (NP / 8) * SBO;
-    constexpr int abytes = 16 * SBO;
+    constexpr int BIT = KC == 32 ? 10 : 8;                  // B-operand pieces per thread: ceil(NP / RPU / 8), NP <= 304 | 512
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int bbytes = NP * row_bytes(KC);
+    constexpr int abytes = 128 * row_bytes(KC);
     uint8_t* sB = smem_raw;                                 // [stage][hi, lo][bbytes]
     uint8_t* sA = sB + 4 * (size_t)bbytes;                  // [stage][hi, lo][abytes]
     __shared__ __align__(8) uint64_t s_mma[2], s_acc;
@@ -474,49 +552,56 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
     const int64_t my_tiles = range < n_tiles ? (n_tiles - range + n_ranges - 1) / n_ranges : 0;
     const int64_t my_chunks = my_tiles * CPT;
     const bool vec = ((reinterpret_cast<uintptr_t>(gt) & 15) == 0) && (((PLANAR ? N : (int64_t)D) & 3) == 0);
-    const int b_units = (NP / 8) * (Q / 4);
+    const int b_units = NP / RPU;
 
-    // PLANAR: gt[d][pixel] is contiguous along the reduction (pixels) -> direct; row-major gt[pixel][d] -> transposed
-    RowTile<KC, !PLANAR> at;
-    float4 bv[BIT];
-    auto load_ab = [&](int64_t ch) {
+    // PLANAR: gt[d][pixel] is contiguous along the reduction (pixels) -> direct; row-major gt[pixel][d] -> transposed.
+    // Two register sets, loads two chunks ahead (see k_sim_tc).
+    struct Regs { RowTile<KC, !PLANAR> at; float4 bv[BIT]; };
+    Regs ra, rb;
+    auto load_ab = [&](Regs& rg, int64_t ch) {
+        if (ch >= my_chunks) return;
         const int64_t tile = range + (ch / CPT) * n_ranges;
         const int64_t p0 = tile * 128 + (ch % CPT) * KC;
-        at.load(gt, PLANAR ? N : (int64_t)D, d0, D, p0, N, vec, tid);
+        rg.at.load(gt, PLANAR ? N : (int64_t)D, d0, D, p0, N, vec, tid);
         const float* bsrc = dsimT + (size_t)tile * NP * 128 + (ch % CPT) * KC;
 #pragma unroll
         for (int i = 0; i < BIT; ++i) {
             const int u = i * 8 + warp;
-            const int r = 8 * (u / (Q / 4)) + (lane & 7), k4 = 4 * (u % (Q / 4)) + (lane >> 3);
-            if (u < b_units) bv[i] = __ldg(reinterpret_cast<const float4*>(bsrc + (size_t)r * 128 + 4 * k4));
+            const int r = u * RPU + lane / Q, k4 = lane % Q;    // a warp instruction reads whole 128-byte (64-byte) rows
+            if (u < b_units) rg.bv[i] = __ldg(reinterpret_cast<const float4*>(bsrc + (size_t)r * 128 + 4 * k4));
         }
     };
-    if (my_chunks > 0) load_ab(0);
+    load_ab(ra, 0);
+    load_ab(rb, 1);
 
     float ss_unused[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t ch = 0; ch < my_chunks; ++ch) {
+    auto step = [&](Regs& rg, int64_t ch) {
         const int s = (int)(ch & 1);
         const uint32_t u = (uint32_t)(ch >> 1);
         if (ch >= 2) wait(smem_u32(&s_mma[s]), (u - 1) & 1);
         const uint32_t b_hi = smem_u32(sB) + (uint32_t)(2 * s) * bbytes, b_lo = b_hi + bbytes;
         const uint32_t a_hi = smem_u32(sA) + (uint32_t)(2 * s) * abytes, a_lo = a_hi + abytes;
-        at.store(a_hi, a_lo, SBO, want_lo, tid, ss_unused);
+        rg.at.store(a_hi, a_lo, want_lo, tid, ss_unused);
 #pragma unroll
         for (int i = 0; i < BIT; ++i) {
             const int uu = i * 8 + warp;
-            const int r = 8 * (uu / (Q / 4)) + (lane & 7), k4 = 4 * (uu % (Q / 4)) + (lane >> 3);
+            const int r = uu * RPU + lane / Q, k4 = lane % Q;
             if (uu < b_units)
-                store_split(b_hi, b_lo, (uint32_t)((r >> 3) * SBO + k4 * LBO + (r & 7) * 16), bv[i].x, bv[i].y, bv[i].z, bv[i].w, want_lo);
+                store_split(b_hi, b_lo, (uint32_t)piece_off(KC, r, k4), rg.bv[i].x, rg.bv[i].y, rg.bv[i].z, rg.bv[i].w, want_lo);
         }
-        if (ch + 1 < my_chunks) load_ab(ch + 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        load_ab(rg, ch + 2);                                // behind the fence: a whole chunk period to land
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;");
-            issue_chunk<KC>(tmem, a_hi, a_lo, b_hi, b_lo, SBO, N0, N1, nterms, ch == 0);
+            issue_chunk<KC>(tmem, a_hi, a_lo, b_hi, b_lo, N0, N1, nterms, ch == 0);
             commit(smem_u32(&s_mma[s]));
             if (ch == my_chunks - 1) commit(smem_u32(&s_acc));
         }
+    };
+    for (int64_t ch = 0; ch < my_chunks; ch += 2) {
+        step(ra, ch);
+        if (ch + 1 < my_chunks) step(rb, ch + 1);
     }
 
     if (my_chunks > 0) {
@@ -544,17 +629,17 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
 
 // The codebook operand of k_sim_tc: lut1 split once into TF32 hi / lo images, chunk by chunk, already in the shared-
 // memory layout (rows >= K and columns >= D are zeros) so that a stage is one bulk copy per image.
-__global__ void __launch_bounds__(256) k_build_wimg(int K, int D, int NP, int KC, int nchunks, int sbo,
+__global__ void __launch_bounds__(256) k_build_wimg(int K, int D, int NP, int KC, int nchunks,
                                                     const float* __restrict__ lut1, uint8_t* __restrict__ img)
 {
-    const int wbytes = (NP / 8) * sbo;
+    const int wbytes = NP * row_bytes(KC);
     const int total = nchunks * NP * KC;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = i / (NP * KC), rk = i % (NP * KC), r = rk / KC, k = rk % KC;
         const int d = c * KC + k;
         const float v = (r < K && d < D) ? lut1[(size_t)r * D + d] : 0.f;
         const uint32_t hi = __float_as_uint(v) & 0xffffe000u;
-        const size_t off = (size_t)c * 2 * wbytes + (size_t)((r >> 3) * sbo + (k >> 2) * LBO + (r & 7) * 16 + (k & 3) * 4);
+        const size_t off = (size_t)c * 2 * wbytes + (size_t)(piece_off(KC, r, k >> 2) + (k & 3) * 4);
         *reinterpret_cast<uint32_t*>(img + off) = hi;
         *reinterpret_cast<float*>(img + off + wbytes) = v - __uint_as_float(hi);
     }
