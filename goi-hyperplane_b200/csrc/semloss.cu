@@ -130,18 +130,23 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane)
 }
 __device__ __forceinline__ int dx_channel(int lane, int n) { return n == 32 ? lane : (lane >> 1); }
 
-// k^ = argmax_k (W x + b)_k per pixel (first maximum, like torch.argmax): the codebook row train.py:156 looks up.  A
-// warp owns a pixel, lane l owns codebook rows l, l + 32, ...; weights staged once per CTA (rows padded with bias -inf).
+// Both logit-side kernels: a warp owns PXB pixels at a time, lane l owns codebook rows k = l, l + 32, ... (KI per lane).
+// A weight row (S floats, LDS.128) is loaded once and used for all PXB pixels -- the one-pixel-at-a-time kernel of
+// round 1 issued one LDS.128 per 4 FMAs and was bound by the shared-memory pipe (l1tex 90 %), not by the FMAs.
+template <int NS4, int KI> struct PixBlock { static constexpr int PXB = (NS4 <= 4 && KI <= 10) ? 4 : 2; };
+
+// k^ = argmax_k (W x + b)_k per pixel (first maximum, like torch.argmax): the codebook row train.py:156 looks up.
+// Weights staged once per CTA (rows padded with bias -inf).
 template <int NS4, int KI>
 __global__ void __launch_bounds__(ROWS_THREADS, 2)
 k_semloss_zarg(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
                const float* __restrict__ W, const float* __restrict__ bias, int* __restrict__ zarg)
 {
-    constexpr int SP = 4 * NS4, WS = SP + 4, KP = 32 * KI;
+    constexpr int SP = 4 * NS4, WS = SP + 4, KP = 32 * KI, PXB = PixBlock<NS4, KI>::PXB;
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);               // [KP][WS]
     float* s_b = s_w + (size_t)KP * WS;                         // [KP]
-    float* s_x = s_b + KP;                                      // [8 warps][2][SP]
+    float* s_x = s_b + KP;                                      // [8 warps][2][PXB][SP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < KP * SP; i += ROWS_THREADS) {
         const int k = i / SP, c = i % SP;
@@ -149,46 +154,63 @@ k_semloss_zarg(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_
     }
     for (int i = tid; i < KP; i += ROWS_THREADS) s_b[i] = i < K ? (bias ? bias[i] : 0.f) : -INFINITY;
     __syncthreads();
+    const int64_t ngroups = (N + PXB - 1) / PXB;
     const int64_t nwarps = (int64_t)gridDim.x * (ROWS_THREADS / 32);
     int par = 0;
-    for (int64_t p = (int64_t)blockIdx.x * (ROWS_THREADS / 32) + warp; p < N; p += nwarps, par ^= 1) {
-        float* xrow = s_x + (warp * 2 + par) * SP;              // double-buffered: no second __syncwarp per pixel
-        for (int c = lane; c < SP; c += 32) xrow[c] = c < S ? x[p * xs_n + c * xs_c] : 0.f;
-        __syncwarp();
-        float xs[SP];
-#pragma unroll
-        for (int q = 0; q < NS4; ++q) {
-            const float4 v = reinterpret_cast<const float4*>(xrow)[q];
-            xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+    for (int64_t gq = (int64_t)blockIdx.x * (ROWS_THREADS / 32) + warp; gq < ngroups; gq += nwarps, par ^= 1) {
+        const int64_t p0 = gq * PXB;
+        float* xg = s_x + (warp * 2 + par) * PXB * SP;          // double-buffered: one __syncwarp per group
+        for (int i = lane; i < PXB * SP; i += 32) {
+            const int px = i / SP, c = i % SP;
+            xg[i] = (c < S && p0 + px < N) ? x[(p0 + px) * xs_n + c * xs_c] : 0.f;
         }
-        float zmax = -INFINITY;
-        int za = 0;
+        __syncwarp();
+        float xs[PXB][SP];
+#pragma unroll
+        for (int px = 0; px < PXB; ++px)
+#pragma unroll
+            for (int q = 0; q < NS4; ++q) {
+                const float4 v = reinterpret_cast<const float4*>(xg + px * SP)[q];
+                xs[px][4 * q] = v.x; xs[px][4 * q + 1] = v.y; xs[px][4 * q + 2] = v.z; xs[px][4 * q + 3] = v.w;
+            }
+        float zmax[PXB];
+        int za[PXB];
+#pragma unroll
+        for (int px = 0; px < PXB; ++px) { zmax[px] = -INFINITY; za[px] = 0; }
 #pragma unroll
         for (int i = 0; i < KI; ++i) {
             const int k = lane + 32 * i;
-            float a = 0.f;
+            float w[SP];
 #pragma unroll
             for (int q = 0; q < NS4; ++q) {
                 const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
-                a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
+                w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
             }
-            a += s_b[k];
-            if (a > zmax) { zmax = a; za = k; }
+            const float bk = s_b[k];
+#pragma unroll
+            for (int px = 0; px < PXB; ++px) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < SP; ++c) a = fmaf(xs[px][c], w[c], a);
+                a += bk;
+                if (a > zmax[px]) { zmax[px] = a; za[px] = k; }      // ascending k: first maximum wins
+            }
         }
-        warp_argmax(zmax, za);
-        if (lane == 0) zarg[p] = za;
+#pragma unroll
+        for (int px = 0; px < PXB; ++px) {
+            warp_argmax(zmax[px], za[px]);
+            if (lane == 0 && p0 + px < N) zarg[p0 + px] = za[px];
+        }
     }
 }
 
 // One pass per pixel over its logit row; see the header of this file.
-// Phase A: a warp owns a pixel, lane l owns codebook rows k = l, l+32, ... (KI values per lane, in registers); the
-//          next pixel's label bits are prefetched while the current one is processed.
+// Phase A: PXB pixels at a time per warp (see above); the label bits of the next group are prefetched.
 // Phase B: the CTA turns the PB staged dz rows into its running dW / db accumulators (thread t owns rows t, t+256).
 // exp is ex2.approx (2 ulp): it produces softmax weights that enter sums of K terms; decisions never depend on it.
-// (The expression order of z, P', dz, dx, dW below is the one of the single-pass kernel of round 1: same numerics.)
+// (The expression order of z, P', dz, dx, dW per pixel is the one of the single-pass kernel of round 1.)
 template <int NS4, int KI>
-__global__ void __launch_bounds__(ROWS_THREADS, (NS4 <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(ROWS_THREADS, 1)
 k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
                const uint32_t* __restrict__ lmask, int64_t Npad, int KW, const float* __restrict__ W,
                const float* __restrict__ bias, float* __restrict__ dL_dx, float* __restrict__ dW,
@@ -196,9 +218,13 @@ k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_
 {
     constexpr int SP = 4 * NS4;                 // padded channels
     constexpr int WS = SP + 4;                  // row stride of the staged weights: LDS.128 conflict-free
-    constexpr int KTT = (KI * 32 + ROWS_THREADS - 1) / ROWS_THREADS;   // codebook rows per thread in phase B
+    constexpr int RB = KI == 10 ? 5 : 4;        // phase B: codebook rows per item,
+    constexpr int KBLK = 32 * KI / RB;          //          row blocks,
+    constexpr int NIT = (KBLK * NS4 + ROWS_THREADS - 1) / ROWS_THREADS;   // items per thread
     constexpr int DXN = SP <= 16 ? 16 : 32;     // dx reduction width
     constexpr int PPW = PB / 8;                 // pixels per warp per batch
+    constexpr int PXB = PixBlock<NS4, KI>::PXB;     // pixels processed jointly
+    static_assert(PPW % PXB == 0, "pixel blocking");
     extern __shared__ float4 smem4[];
     // Codebook rows are padded to KP = 32 KI with zero weights and a bias of -inf: a padded row has logit -inf,
     // softmax weight 0 and gradient 0, so the per-lane loops below run without any k < K control flow.
@@ -218,132 +244,171 @@ k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_
 
     const float cl = 100.0f / ((float)N * (float)K);            // d(50 * MSE)/d(P') = 2 * 50 / (N K) * (P' - L)
 
-    float accw[KTT][SP], accb[KTT];
+    // phase-B ownership: item = (block of RB codebook rows, channel quad); lanes walk consecutive row blocks (their dz
+    // reads are conflict-free: stride 5 words, or one LDS.128 at RB = 4), a warp shares the channel quad (broadcast)
+    float accw[NIT][RB][4], accb[NIT][RB];
 #pragma unroll
-    for (int kk = 0; kk < KTT; ++kk) {
-        accb[kk] = 0.f;
+    for (int it = 0; it < NIT; ++it)
 #pragma unroll
-        for (int c = 0; c < SP; ++c) accw[kk][c] = 0.f;
-    }
+        for (int r = 0; r < RB; ++r) { accb[it][r] = 0.f; accw[it][r][0] = accw[it][r][1] = accw[it][r][2] = accw[it][r][3] = 0.f; }
     double l_lab = 0.0;
 
     const int64_t nbatch = (N + PB - 1) / PB;
-    // prefetch register: word `lane` of the next pixel's label bits (word i covers codebook rows 32 i .. 32 i + 31)
-    uint32_t lw = 0;
-    auto prefetch = [&](int64_t p) {
-        lw = (p < N && lane < KW) ? __ldg(lmask + (size_t)lane * Npad + (size_t)p) : 0u;
+    // prefetch registers: word `lane` of the label bits of the next group's pixels (word i = codebook rows 32 i ..)
+    uint32_t lw[PXB];
+    auto prefetch = [&](int64_t p0) {
+#pragma unroll
+        for (int px = 0; px < PXB; ++px)
+            lw[px] = (p0 + px < N && lane < KW) ? __ldg(lmask + (size_t)lane * Npad + (size_t)(p0 + px)) : 0u;
     };
     prefetch((int64_t)blockIdx.x * PB + warp * PPW);
 
     for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
         // ---------------- phase A ----------------
-        for (int pp = 0; pp < PPW; ++pp) {
-            const int pl = warp * PPW + pp;                      // pixel slot in the batch
-            const int64_t p = bt * PB + pl;
-            float* dzrow = s_dz + (size_t)pl * KP;
-            float* xrow = s_x + pl * SP;
-            const int64_t pnext = (pp + 1 < PPW) ? p + 1 : (bt + gridDim.x) * PB + warp * PPW;
-            if (p >= N) {                                        // ragged tail: contributes nothing
-                for (int k = lane; k < KP; k += 32) dzrow[k] = 0.f;
-                for (int c = lane; c < SP; c += 32) xrow[c] = 0.f;
-                prefetch(pnext);
-                continue;
+        for (int pg = 0; pg < PPW; pg += PXB) {
+            const int pl0 = warp * PPW + pg;                     // first pixel slot of the group in the batch
+            const int64_t p0 = bt * PB + pl0;
+            float* xg = s_x + pl0 * SP;
+            for (int i = lane; i < PXB * SP; i += 32) {
+                const int px = i / SP, c = i % SP;
+                xg[i] = (c < S && p0 + px < N) ? x[(p0 + px) * xs_n + c * xs_c] : 0.f;
             }
-            for (int c = lane; c < SP; c += 32) xrow[c] = c < S ? x[p * xs_n + c * xs_c] : 0.f;
             // label bits of this lane's codebook rows: bit i <-> row lane + 32 i
-            unsigned lmask_l = 0;
+            unsigned lmask_l[PXB];
 #pragma unroll
-            for (int i = 0; i < KI; ++i) lmask_l |= ((__shfl_sync(0xffffffffu, lw, i) >> lane) & 1u) << i;
-            prefetch(pnext);
+            for (int px = 0; px < PXB; ++px) {
+                lmask_l[px] = 0;
+#pragma unroll
+                for (int i = 0; i < KI; ++i) lmask_l[px] |= ((__shfl_sync(0xffffffffu, lw[px], i) >> lane) & 1u) << i;
+            }
+            prefetch((pg + PXB < PPW) ? p0 + PXB : (bt + gridDim.x) * PB + warp * PPW);
             __syncwarp();
-            float xs[SP];
-#pragma unroll
-            for (int q = 0; q < NS4; ++q) {
-                const float4 v = reinterpret_cast<const float4*>(xrow)[q];
-                xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
-            }
 
-            // logits of this lane's codebook rows and their maximum
-            float z[KI];
-            float zmax = -INFINITY;
+            // logits of this lane's codebook rows for the PXB pixels, and their maxima
+            float z[PXB][KI], zmax[PXB];
+            {
+                float xs[PXB][SP];
 #pragma unroll
-            for (int i = 0; i < KI; ++i) {
-                const int k = lane + 32 * i;
-                float a = 0.f;
+                for (int px = 0; px < PXB; ++px) {
+                    zmax[px] = -INFINITY;
 #pragma unroll
-                for (int q = 0; q < NS4; ++q) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                    a = fmaf(xs[4 * q], w4.x, a); a = fmaf(xs[4 * q + 1], w4.y, a);
-                    a = fmaf(xs[4 * q + 2], w4.z, a); a = fmaf(xs[4 * q + 3], w4.w, a);
+                    for (int q = 0; q < NS4; ++q) {
+                        const float4 v = reinterpret_cast<const float4*>(xg + px * SP)[q];
+                        xs[px][4 * q] = v.x; xs[px][4 * q + 1] = v.y; xs[px][4 * q + 2] = v.z; xs[px][4 * q + 3] = v.w;
+                    }
                 }
-                z[i] = a + s_b[k];
-                zmax = fmaxf(zmax, z[i]);
-                asm volatile("" ::: "memory");                   // keep the weight loads of later rows from piling up in registers
-            }
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-
-            // softmax numerators, computed once: z <- exp(z - zmax)
-            float zsum = 0.f;
+                for (int i = 0; i < KI; ++i) {
+                    const int k = lane + 32 * i;
+                    float w[SP];
 #pragma unroll
-            for (int i = 0; i < KI; ++i) {
-                z[i] = __expf(z[i] - zmax);                      // padded rows: exp(-inf) = 0
-                zsum += z[i];
-            }
-            zsum = warp_sum(zsum);
-            const float zinv = 1.f / zsum;
-            // lab = sum (P' - L)^2, dot = sum P' g
-            float lab = 0.f, dot = 0.f;
+                    for (int q = 0; q < NS4; ++q) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                        w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+                    }
+                    const float bk = s_b[k];
 #pragma unroll
-            for (int i = 0; i < KI; ++i) {
-                const float Pz = z[i] * zinv;
-                const float diff = Pz - ((lmask_l & (1u << i)) ? 1.f : 0.f);
-                lab = fmaf(diff, diff, lab);
-                dot = fmaf(Pz, cl * diff, dot);
-                z[i] = Pz;
-            }
-            lab = warp_sum(lab); dot = warp_sum(dot);
-            if (lane == 0) l_lab += (double)lab;
-
-            // gradients: dz -> staged row + dx partials
-            float dxp[DXN];
+                    for (int px = 0; px < PXB; ++px) {
+                        float a = 0.f;
 #pragma unroll
-            for (int c = 0; c < DXN; ++c) dxp[c] = 0.f;
-#pragma unroll
-            for (int i = 0; i < KI; ++i) {
-                const int k = lane + 32 * i;
-                const float Pz = z[i];
-                const float dz = Pz * (cl * (Pz - ((lmask_l & (1u << i)) ? 1.f : 0.f)) - dot);   // 0 for padded rows
-                dzrow[k] = dz;
-#pragma unroll
-                for (int q = 0; q < NS4; ++q) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                    dxp[4 * q] = fmaf(dz, w4.x, dxp[4 * q]); dxp[4 * q + 1] = fmaf(dz, w4.y, dxp[4 * q + 1]);
-                    dxp[4 * q + 2] = fmaf(dz, w4.z, dxp[4 * q + 2]); dxp[4 * q + 3] = fmaf(dz, w4.w, dxp[4 * q + 3]);
+                        for (int c = 0; c < SP; ++c) a = fmaf(xs[px][c], w[c], a);
+                        z[px][i] = a + bk;
+                        zmax[px] = fmaxf(zmax[px], z[px][i]);
+                    }
                 }
-                asm volatile("" ::: "memory");
             }
+            // per pixel: softmax, loss partial, dz (overwrites z)
+#pragma unroll
+            for (int px = 0; px < PXB; ++px) {
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) zmax[px] = fmaxf(zmax[px], __shfl_xor_sync(0xffffffffu, zmax[px], o));
+                float zsum = 0.f;
+#pragma unroll
+                for (int i = 0; i < KI; ++i) {
+                    z[px][i] = __expf(z[px][i] - zmax[px]);      // padded rows: exp(-inf) = 0
+                    zsum += z[px][i];
+                }
+                zsum = warp_sum(zsum);
+                const float zinv = 1.f / zsum;
+                float lab = 0.f, dot = 0.f;                      // lab = sum (P' - L)^2, dot = sum P' g
+#pragma unroll
+                for (int i = 0; i < KI; ++i) {
+                    const float Pz = z[px][i] * zinv;
+                    const float diff = Pz - ((lmask_l[px] & (1u << i)) ? 1.f : 0.f);
+                    lab = fmaf(diff, diff, lab);
+                    dot = fmaf(Pz, cl * diff, dot);
+                    z[px][i] = Pz;
+                }
+                lab = warp_sum(lab); dot = warp_sum(dot);
+                const bool live = p0 + px < N;                   // ragged tail: contributes nothing
+                if (lane == 0 && live) l_lab += (double)lab;
+                float* dzrow = s_dz + (size_t)(pl0 + px) * KP;
+#pragma unroll
+                for (int i = 0; i < KI; ++i) {
+                    const float Pz = z[px][i];
+                    const float dz = live ? Pz * (cl * (Pz - ((lmask_l[px] & (1u << i)) ? 1.f : 0.f)) - dot) : 0.f;   // 0 for padded rows
+                    z[px][i] = dz;
+                    dzrow[lane + 32 * i] = dz;
+                }
+            }
+            // dx partials, PXB / 2 pixels per pass over the weight rows (the partial sums of all PXB pixels at once would
+            // not fit the register file next to the phase-B accumulators)
             if (dL_dx) {
-                const float v = warp_transpose_sum<DXN>(dxp, lane);
-                const int c = dx_channel(lane, DXN);
-                if ((DXN == 32 || (lane & 1) == 0) && c < S) dL_dx[p * xs_n + c * xs_c] = v;
+                constexpr int DPX = PXB / 2;
+#pragma unroll
+                for (int h = 0; h < PXB; h += DPX) {
+                    float dxp[DPX][DXN];
+#pragma unroll
+                    for (int px = 0; px < DPX; ++px)
+#pragma unroll
+                        for (int c = 0; c < DXN; ++c) dxp[px][c] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < KI; ++i) {
+                        const int k = lane + 32 * i;
+                        float w[SP];
+#pragma unroll
+                        for (int q = 0; q < NS4; ++q) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
+                            w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+                        }
+#pragma unroll
+                        for (int px = 0; px < DPX; ++px)
+#pragma unroll
+                            for (int c = 0; c < SP; ++c) dxp[px][c] = fmaf(z[h + px][i], w[c], dxp[px][c]);
+                    }
+#pragma unroll
+                    for (int px = 0; px < DPX; ++px) {
+                        const float v = warp_transpose_sum<DXN>(dxp[px], lane);
+                        const int c = dx_channel(lane, DXN);
+                        if ((DXN == 32 || (lane & 1) == 0) && c < S && p0 + h + px < N) dL_dx[(p0 + h + px) * xs_n + c * xs_c] = v;
+                    }
+                }
             }
         }
         __syncthreads();
         // ---------------- phase B: dW += dz^T x, db += dz over the batch ----------------
         if (dW) {
 #pragma unroll
-            for (int kk = 0; kk < KTT; ++kk) {
-                const int k = tid + ROWS_THREADS * kk;
-                if (k < K) {
+            for (int it = 0; it < NIT; ++it) {
+                const int item = tid + ROWS_THREADS * it;
+                if (item < KBLK * NS4) {
+                    const int kb = item % KBLK, quad = item / KBLK;
                     for (int pl = 0; pl < PB; ++pl) {
-                        const float d = s_dz[(size_t)pl * KP + k];
-                        accb[kk] += d;
+                        const float* dzr = s_dz + (size_t)pl * KP + RB * kb;
+                        float d[RB];
+                        if (RB == 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(dzr);
+                            d[0] = t4.x; d[1] = t4.y; d[2] = t4.z; d[3] = t4.w;
+                        } else {
 #pragma unroll
-                        for (int q = 0; q < NS4; ++q) {
-                            const float4 v = reinterpret_cast<const float4*>(s_x + pl * SP)[q];
-                            accw[kk][4 * q] = fmaf(d, v.x, accw[kk][4 * q]); accw[kk][4 * q + 1] = fmaf(d, v.y, accw[kk][4 * q + 1]);
-                            accw[kk][4 * q + 2] = fmaf(d, v.z, accw[kk][4 * q + 2]); accw[kk][4 * q + 3] = fmaf(d, v.w, accw[kk][4 * q + 3]);
+                            for (int r = 0; r < RB; ++r) d[r] = dzr[r];
+                        }
+                        const float4 v = reinterpret_cast<const float4*>(s_x + pl * SP)[quad];
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) {
+                            accb[it][r] += d[r];
+                            accw[it][r][0] = fmaf(d[r], v.x, accw[it][r][0]); accw[it][r][1] = fmaf(d[r], v.y, accw[it][r][1]);
+                            accw[it][r][2] = fmaf(d[r], v.z, accw[it][r][2]); accw[it][r][3] = fmaf(d[r], v.w, accw[it][r][3]);
                         }
                     }
                 }
@@ -354,13 +419,20 @@ k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_
 
     if (dW) {
 #pragma unroll
-        for (int kk = 0; kk < KTT; ++kk) {
-            const int k = tid + ROWS_THREADS * kk;
-            if (k < K) {
-                if (db) atomicAdd(db + k, accb[kk]);
+        for (int it = 0; it < NIT; ++it) {
+            const int item = tid + ROWS_THREADS * it;
+            if (item < KBLK * NS4) {
+                const int kb = item % KBLK, quad = item / KBLK;
 #pragma unroll
-                for (int c = 0; c < SP; ++c)
-                    if (c < S) atomicAdd(dW + (size_t)k * S + c, accw[kk][c]);
+                for (int r = 0; r < RB; ++r) {
+                    const int k = RB * kb + r;
+                    if (k < K) {
+                        if (db && quad == 0) atomicAdd(db + k, accb[it][r]);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (4 * quad + c < S) atomicAdd(dW + (size_t)k * S + 4 * quad + c, accw[it][r][c]);
+                    }
+                }
             }
         }
     }
@@ -495,11 +567,11 @@ cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const G
     constexpr int KP = 32 * KI;                                 // padded codebook rows (see the kernel)
     const int sms = device_sms();
     {
-        const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + 16 * SP);
+        const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + 16 * PixBlock<NS4, KI>::PXB * SP);
         auto kern = k_semloss_zarg<NS4, KI>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int64_t grid = (a.N + 7) / 8;
+        int64_t grid = (a.N + 8 * PixBlock<NS4, KI>::PXB - 1) / (8 * PixBlock<NS4, KI>::PXB);
         if (grid > (int64_t)sms * 2) grid = (int64_t)sms * 2;
         kern<<<(unsigned)grid, ROWS_THREADS, smem, st>>>(a.N, a.S, a.K, a.x, a.x_stride_n, a.x_stride_c, a.mlp_weight,
                                                         a.mlp_bias, w.zarg);
@@ -513,7 +585,7 @@ cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const G
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t nbatch = (a.N + PB - 1) / PB;
-    int64_t grid = (int64_t)sms * (NS4 <= 4 ? 2 : 1);
+    int64_t grid = sms;                                         // one CTA per SM (the pixel-blocked phase A is register-heavy)
     if (grid > nbatch) grid = nbatch;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, ROWS_THREADS, smem, st>>>(a.N, a.S, a.K, a.x, a.x_stride_n, a.x_stride_c, w.lmask, g.Npad, g.KW,
