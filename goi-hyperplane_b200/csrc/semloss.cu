@@ -254,12 +254,20 @@ k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_
     double l_lab = 0.0;
 
     const int64_t nbatch = (N + PB - 1) / PB;
-    // prefetch registers: word `lane` of the label bits of the next group's pixels (word i = codebook rows 32 i ..)
+    // prefetch registers of the next group's pixels: word `lane` of the label bits (word i = codebook rows 32 i ..) and
+    // this lane's share of the PXB x SP feature values
+    constexpr int XPL = (PXB * SP + 31) / 32;
     uint32_t lw[PXB];
+    float xpre[XPL];
     auto prefetch = [&](int64_t p0) {
 #pragma unroll
         for (int px = 0; px < PXB; ++px)
             lw[px] = (p0 + px < N && lane < KW) ? __ldg(lmask + (size_t)lane * Npad + (size_t)(p0 + px)) : 0u;
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) {
+            const int i = lane + 32 * j, px = i / SP, c = i % SP;
+            xpre[j] = (i < PXB * SP && c < S && p0 + px < N) ? __ldg(x + (p0 + px) * xs_n + c * xs_c) : 0.f;
+        }
     };
     prefetch((int64_t)blockIdx.x * PB + warp * PPW);
 
@@ -269,10 +277,9 @@ k_semloss_rows(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_
             const int pl0 = warp * PPW + pg;                     // first pixel slot of the group in the batch
             const int64_t p0 = bt * PB + pl0;
             float* xg = s_x + pl0 * SP;
-            for (int i = lane; i < PXB * SP; i += 32) {
-                const int px = i / SP, c = i % SP;
-                xg[i] = (c < S && p0 + px < N) ? x[(p0 + px) * xs_n + c * xs_c] : 0.f;
-            }
+#pragma unroll
+            for (int j = 0; j < XPL; ++j)
+                if (lane + 32 * j < PXB * SP) xg[lane + 32 * j] = xpre[j];
             // label bits of this lane's codebook rows: bit i <-> row lane + 32 i
             unsigned lmask_l[PXB];
 #pragma unroll

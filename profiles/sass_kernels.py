@@ -22,10 +22,10 @@ for line in out.splitlines():
     if m and cur:
         hist[cur][m.group(1)] += 1
 demangle = subprocess.run(["c++filt"] + list(hist), capture_output=True, text=True).stdout.splitlines()
-KEY = ("HMMA", "UTCHMMA", "LDTM", "UTCBAR", "REDG", "RED", "ATOMG", "LDGSTS", "FFMA2", "MUFU", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "VOTE")
+KEY = ("HMMA", "UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "SYNCS", "REDG", "RED", "ATOMG", "LDGSTS", "FFMA2", "MUFU", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "VOTE")
 for name, pretty in sorted(zip(hist, demangle), key=lambda kv: kv[1]):
     if not pat.search(pretty):
         continue
     h = hist[name]
-    short = re.sub(r"\(.*", "", pretty).replace("void ", "")
+    short = re.sub(r"\(.*", "", pretty.replace("(anonymous namespace)::", "")).replace("void ", "")
     print(f"{short:48s} {sum(h.values()):6d} instr | " + " ".join(f"{k}={h[k]}" for k in KEY if h[k]))

@@ -84,6 +84,27 @@ def test_semloss_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
         assert getattr(sl.goi_semloss_args, f).offset == int(out[f]), f
 
 
+def test_semloss_library_is_self_contained_and_uses_the_blackwell_tensor_cores():
+    """Row f2 without library GEMMs: libgoi_semloss.so must not depend on cuBLAS, and its two contractions must be the
+    hand-written tcgen05 kernels (SASS: UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UBLKCP = cp.async.bulk)."""
+    import shutil
+    import subprocess
+    from goi_b200 import semantic_loss as sl
+    path = os.path.abspath(sl.LIB_PATH)
+    needed = subprocess.run(["readelf", "-d", path], capture_output=True, text=True, check=True).stdout
+    assert "cublas" not in needed.lower(), needed
+    src = open(os.path.join(ROOT, "goi-hyperplane_b200", "csrc", "semloss.cu")).read()
+    assert "cublas" not in src.lower().replace("no library gemm", "")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, check=True).stdout
+    for kernel in ("k_sim_tc", "k_dlut_tc"):
+        assert kernel in sass, kernel
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+
+
 def test_product_never_imports_the_oracle():
     src = open(os.path.join(ROOT, "goi-hyperplane_b200", "goi_b200", "semantic_loss.py")).read()
     assert "oracle" not in src.replace("no CPU/eager fallback", "")
