@@ -4,8 +4,8 @@
     loss.backward()        # gradients reach the rendered features (-> the rasterizer), the MLP and the codebook
 
 replaces the reference's ~25 torch ops and their autograd graph (about ten [HW,300] temporaries + two [HW,256] ones per
-iteration) with include/goi_semloss.h: two plain GEMMs and one fused row kernel whose only [HW,300] array is the
-similarity matrix, overwritten in place by its own gradient.  `sem_feature` is the render's planar [S,H,W] output and
+iteration) with include/goi_semloss.h: both contractions are hand-written tcgen05 kernels (the similarity matrix lives in
+tensor memory and never reaches HBM; the only [HW,300] array is its gradient) around two fused row kernels.  `sem_feature` is the render's planar [S,H,W] output and
 `gt` the dataset's planar [D,H,W] target (both read in place; the reference permutes + reshapes both, train.py:142,147),
 or [N,S] / [N,D] matrices.  There is no CPU/eager fallback: a missing library is an ImportError.
 """
@@ -46,7 +46,7 @@ def lib() -> C.CDLL:
         path = os.path.abspath(LIB_PATH)
         if not os.path.exists(path):
             raise ImportError(f"{path} not found: build it with `python goi-hyperplane_b200/build.py` "
-                              "(nvcc sm_100a + cuBLAS). The semantic loss has no CPU/eager fallback.")
+                              "(nvcc sm_100a). The semantic loss has no CPU/eager fallback.")
         h = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(h, name)

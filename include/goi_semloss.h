@@ -16,19 +16,21 @@
  *     loss = lab + sl + 0.3 sl1 + recc                          :163
  *
  * and returns dloss/d{sem_feature, MLP weight, MLP bias, lut}.  The reference materialises about ten
- * [N,K] temporaries (N = H*W pixels, K = 300) plus two [N,256] ones per iteration; here the only [N,K]
- * array is the similarity matrix itself, overwritten in place by its own gradient:
+ * [N,K] temporaries (N = H*W pixels, K = 300) plus two [N,256] ones per iteration; here the similarity matrix
+ * lives in tensor memory and the only [N,K] array in HBM is its gradient:
  *
- *     1. k_lut_normalize, k_gt_inv_norms                      (tiny / one read of gt)
- *     2. G = gt @ lut1^T                                      cuBLAS GEMM (a plain library GEMM)
- *     3. k_semloss_rows: per pixel, ONE pass: MLP logits + softmax, row max / arg-max / label, entropy,
- *        all four loss terms, d/dlogits -> dL/dsem_feature, dL/dW, dL/db, and d/dsim written over G
- *     4. dlut1 = dsim^T @ gt                                  cuBLAS GEMM
- *     5. k_lut_normalize_bwd, k_semloss_finalize
+ *     1. k_lut_normalize, k_build_wimg                        (tiny: codebook rows, their TF32 hi / lo operand images)
+ *     2. k_semloss_zarg: argmax of the MLP logits             (reads x)
+ *     3. k_sim_tc: sim = gt/|gt| @ lut1^T on tcgen05 (accumulators in TMEM), then per pixel out of tensor memory:
+ *        row max / arg-max / label bits, entropy, the similarity-side loss terms and d/dsim (written once)
+ *     4. k_semloss_rows: per pixel, ONE pass: MLP logits + softmax, (P' - L)^2, d/dlogits -> dL/dsem_feature,
+ *        dL/dW, dL/db
+ *     5. k_dlut_tc: dlut1 = dsim^T @ gt on tcgen05           (accumulators in TMEM, split over the pixel axis)
+ *     6. k_lut_normalize_bwd, k_semloss_finalize
  *
- * `precision`: GOI_SEMLOSS_FP32 runs the two GEMMs in true fp32 like the reference (torch's default
- * allow_tf32 = False for matmul); GOI_SEMLOSS_TF32 lets cuBLAS use the TF32 tensor cores (inputs rounded to
- * 10 mantissa bits, fp32 accumulate).
+ * No library GEMM.  `precision`: GOI_SEMLOSS_FP32 evaluates the two contractions with the x = hi + lo TF32 split
+ * (three tensor-core products, ~2^-21: fp32-accurate like the reference, torch's default allow_tf32 = False for
+ * matmul); GOI_SEMLOSS_TF32 runs the hi product only (inputs rounded to 10 mantissa bits, fp32 accumulate).
  *
  * Conventions: device pointers, contiguous f32, caller-owned memory and workspace, the caller's stream; returns 0 or
  * a negative status and goi_semloss_last_error() holds a message (same style as goi_raster.h).
