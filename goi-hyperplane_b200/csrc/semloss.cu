@@ -469,7 +469,8 @@ __global__ void k_semloss_finalize(int64_t N, int K, const Accum* acc, float* lo
 // ---- problem geometry of the tensor-core kernels and workspace carving ------------------------------------------
 struct Geometry {
     int NP;            // codebook rows padded to 16 accumulator columns
-    int KC;            // reduction elements per staged chunk: 32, or 16 when the codebook is longer than 304 rows
+    int KC;            // reduction elements per staged chunk (16 or 32)
+    int ns;            // operand stages that fit in shared memory (2 .. 4)
     int nchunks;       // chunks of the codebook width (k_sim_tc)
     int wbytes;        // one codebook image of one chunk
     int KW;            // label words per pixel
@@ -480,13 +481,19 @@ Geometry geometry(int64_t N, int K, int D)
 {
     Geometry g{};
     g.NP = ((K + 15) / 16) * 16;
+    // 32-element chunks (two stages of 110 KB at K = 300) wherever they fit: four stages of 16-element chunks were
+    // measured slower (8.97 vs 7.77 ms at 1.6 Mpx: twice the barriers and MMA batches of two k-steps)
     g.KC = g.NP <= 304 ? 32 : 16;
     g.nchunks = (D + g.KC - 1) / g.KC;
     g.wbytes = g.NP * tc5::row_bytes(g.KC);
     g.KW = (g.NP + 31) / 32;
     g.ntiles = (N + 127) / 128;
     g.Npad = g.ntiles * 128;
-    g.smem = (size_t)4 * g.wbytes + (size_t)4 * 128 * tc5::row_bytes(g.KC) + 1024;   // + alignment slack
+    const size_t stage = (size_t)2 * g.wbytes + (size_t)2 * 128 * tc5::row_bytes(g.KC);
+    g.ns = (int)((size_t)(222 * 1024) / stage);
+    if (g.ns > tc5::MAX_STAGES) g.ns = tc5::MAX_STAGES;
+    if (g.ns < 2) g.ns = 2;
+    g.smem = (size_t)g.ns * stage + 1024;                   // + alignment slack
     return g;
 }
 
@@ -537,7 +544,7 @@ cudaError_t launch_sim_t(const goi_semloss_args& a, const Workspace& w, const Ge
     const int sms = device_sms();
     const unsigned grid = (unsigned)(g.ntiles < sms ? g.ntiles : sms);
     kern<<<grid, tc5::THREADS, g.smem, st>>>(a.N, a.D, a.K, g.NP, g.nchunks, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
-                                             a.anneal_t, a.gt, w.wimg, w.zarg, w.dsimT, w.lmask, g.Npad, &w.acc->sim);
+                                             a.anneal_t, a.gt, w.wimg, w.zarg, w.dsimT, w.lmask, g.Npad, &w.acc->sim, g.ns);
     return cudaGetLastError();
 }
 cudaError_t launch_sim(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
@@ -558,7 +565,7 @@ cudaError_t launch_dlut_t(const goi_semloss_args& a, const Workspace& w, const G
     if (n_ranges < 1) n_ranges = 1;                             // read the same dsimT tiles at about the same time (L2)
     if (n_ranges > g.ntiles) n_ranges = g.ntiles;
     kern<<<(unsigned)(n_ranges * n_slices), tc5::THREADS, g.smem, st>>>(a.N, a.D, a.K, g.NP, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
-                                                                       n_slices, a.gt, w.dsimT, w.dlut1);
+                                                                       n_slices, a.gt, w.dsimT, w.dlut1, g.ns);
     return cudaGetLastError();
 }
 cudaError_t launch_dlut(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)

@@ -29,6 +29,7 @@
 namespace tc5 {
 
 constexpr int THREADS = 256;
+constexpr int MAX_STAGES = 4;                               // operand stages (each: hi + lo images of both operands)
 __host__ __device__ constexpr int row_bytes(int kc) { return 4 * kc; }                      // one operand row of one chunk
 __host__ __device__ constexpr int swz(int kc, int r) { return kc == 32 ? (r & 7) : ((r >> 1) & 3); }
 // byte offset of the 16-byte piece c (reduction elements 4c .. 4c+3) of row r inside an operand image
@@ -286,15 +287,15 @@ template <int KC, bool PLANAR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_anneal, const float* __restrict__ gt,
          const uint8_t* __restrict__ wimg, const int* __restrict__ zarg, float* __restrict__ dsimT,
-         uint32_t* __restrict__ lmask, int64_t Npad, SimStats* __restrict__ stats)
+         uint32_t* __restrict__ lmask, int64_t Npad, SimStats* __restrict__ stats, int ns)
 {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned
     const int wbytes = NP * row_bytes(KC);                  // one codebook image (hi or lo) of one chunk
     constexpr int xbytes = 128 * row_bytes(KC);             // one gt image
     uint8_t* sW = smem_raw;                                 // [stage][hi, lo][wbytes]
-    uint8_t* sX = sW + 4 * (size_t)wbytes;                  // [stage][hi, lo][xbytes]
-    __shared__ __align__(8) uint64_t s_wfull[2], s_mma[2], s_acc;
+    uint8_t* sX = sW + 2 * (size_t)ns * wbytes;             // [stage][hi, lo][xbytes]; ns = 2 .. MAX_STAGES stages
+    __shared__ __align__(8) uint64_t s_wfull[MAX_STAGES], s_mma[MAX_STAGES], s_acc;
     __shared__ uint32_t s_tmem;
     __shared__ float s_ss[128];
     __shared__ float s_pv[2][128], s_ps[2][128], s_pw[2][128];
@@ -304,7 +305,7 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
     const bool want_lo = nterms == 3;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_mma[s], 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_mma[s], 1); }
         mbar_init(&s_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -342,9 +343,9 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
     for (int64_t it = 0; it < my_tiles; ++it, tile += gridDim.x) {
         float ss[4] = {0.f, 0.f, 0.f, 0.f};
         for (int c = 0; c < nchunks; ++c, ++g) {
-            const int s = (int)(g & 1);
-            const uint32_t u = g >> 1;
-            if (g >= 2) wait(smem_u32(&s_mma[s]), (u - 1) & 1);     // the MMAs that read this stage have completed
+            const int s = (int)(g % (uint32_t)ns);
+            const uint32_t u = g / (uint32_t)ns;
+            if (g >= (uint32_t)ns) wait(smem_u32(&s_mma[s]), (u - 1) & 1);     // the MMAs that read this stage have completed
             const uint32_t w_hi = smem_u32(sW) + (uint32_t)(2 * s) * wbytes, w_lo = w_hi + wbytes;
             const uint32_t x_hi = smem_u32(sX) + (uint32_t)(2 * s) * xbytes, x_lo = x_hi + xbytes;
             if (tid == 0) {
@@ -354,11 +355,11 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
                 bulk_g2s(w_hi, src, (uint32_t)wbytes, bar);
                 if (want_lo) bulk_g2s(w_lo, src + wbytes, (uint32_t)wbytes, bar);
             }
-            if (s == 0) xa.store(x_hi, x_lo, want_lo, tid, ss); else xb.store(x_hi, x_lo, want_lo, tid, ss);
+            if ((g & 1) == 0) xa.store(x_hi, x_lo, want_lo, tid, ss); else xb.store(x_hi, x_lo, want_lo, tid, ss);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
             __syncthreads();
             // behind the fence (a fence in front of the loads would wait for them to land)
-            if (s == 0) load_x(xa, it, c + 2); else load_x(xb, it, c + 2);
+            if ((g & 1) == 0) load_x(xa, it, c + 2); else load_x(xb, it, c + 2);
             if (tid == 0) {
                 wait(smem_u32(&s_wfull[s]), u & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -515,7 +516,7 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
 template <int KC, bool PLANAR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float* __restrict__ gt,
-          const float* __restrict__ dsimT, float* __restrict__ dlut1)
+          const float* __restrict__ dsimT, float* __restrict__ dlut1, int ns)
 {
     constexpr int Q = KC / 4, RPU = 32 / Q;                 // pieces per row; rows per warp instruction
     constexpr int CPT = 128 / KC;                           // chunks per pixel tile
@@ -525,8 +526,8 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
     const int bbytes = NP * row_bytes(KC);
     constexpr int abytes = 128 * row_bytes(KC);
     uint8_t* sB = smem_raw;                                 // [stage][hi, lo][bbytes]
-    uint8_t* sA = sB + 4 * (size_t)bbytes;                  // [stage][hi, lo][abytes]
-    __shared__ __align__(8) uint64_t s_mma[2], s_acc;
+    uint8_t* sA = sB + 2 * (size_t)ns * bbytes;             // [stage][hi, lo][abytes]
+    __shared__ __align__(8) uint64_t s_mma[MAX_STAGES], s_acc;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
@@ -535,7 +536,7 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
     const int64_t d0 = (int64_t)slice * 128;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) mbar_init(&s_mma[s], 1);
+        for (int s = 0; s < MAX_STAGES; ++s) mbar_init(&s_mma[s], 1);
         mbar_init(&s_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -576,9 +577,9 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
 
     float ss_unused[4] = {0.f, 0.f, 0.f, 0.f};
     auto step = [&](Regs& rg, int64_t ch) {
-        const int s = (int)(ch & 1);
-        const uint32_t u = (uint32_t)(ch >> 1);
-        if (ch >= 2) wait(smem_u32(&s_mma[s]), (u - 1) & 1);
+        const int s = (int)(ch % ns);
+        const uint32_t u = (uint32_t)(ch / ns);
+        if (ch >= ns) wait(smem_u32(&s_mma[s]), (u - 1) & 1);
         const uint32_t b_hi = smem_u32(sB) + (uint32_t)(2 * s) * bbytes, b_lo = b_hi + bbytes;
         const uint32_t a_hi = smem_u32(sA) + (uint32_t)(2 * s) * abytes, a_lo = a_hi + abytes;
         rg.at.store(a_hi, a_lo, want_lo, tid, ss_unused);

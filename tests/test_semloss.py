@@ -169,6 +169,22 @@ def test_cuda_matches_oracle(N, S, K, D, it):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N,S,K,D", [(4099, 16, 300, 256), (515, 7, 33, 10), (130, 32, 512, 64)])
+def test_cuda_planar_ragged_sizes_match_oracle(N, S, K, D):
+    """Planar [S,1,N] / [D,1,N] inputs whose pixel count is not a multiple of 4 (no 16-byte loads along the pixel axis),
+    codebook widths that are not a multiple of the staged chunk, partial last tiles: the scalar-load and zero-padding
+    paths of the tensor-core kernels."""
+    g = torch.Generator().manual_seed(N * 7 + D)
+    x = torch.randn(N, S, generator=g)
+    W, b = torch.randn(K, S, generator=g) * 0.4, torch.randn(K, generator=g) * 0.1
+    lut = torch.randn(K, D, generator=g) * 0.5 + 0.1
+    gt = lut[torch.randint(0, K, (N,), generator=g)] + 0.3 * torch.randn(N, D, generator=g)
+    ref = semantic_loss_reference(x, W, b, lut, gt, t=2.0, dtype=torch.float64)
+    cu = run_cuda(x, W, b, lut, gt, 2000, planar_hw=(1, N))
+    check(cu, {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in ref.items()})
+
+
+@pytest.mark.gpu
 def test_tf32_gemms_stay_close_and_scale_with_upstream_gradient():
     N, S, K, D = 20000, 16, 300, 256
     g = torch.Generator().manual_seed(5)
