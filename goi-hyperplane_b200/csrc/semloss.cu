@@ -3,7 +3,7 @@
 //
 // Data flow (N pixels, K codebook rows, D codebook width, S rendered channels):
 //     lut1 = lut / |lut|                          k_lut_normalize, k_build_wimg   K blocks; TF32 hi / lo operand images
-//     k^ = argmax (W x + b)                       k_semloss_zarg             reads x (4NS)
+//     k^ = argmax (W x + b)                       k_zarg_tc (semloss_tc.cuh) tcgen05 projection + arg-max sweep out of TMEM; reads x (4NS)
 //     sim = (gt / |gt|) @ lut1^T  in TMEM         k_sim_tc (semloss_tc.cuh)  tcgen05.mma, 3 x TF32 = fp32-accurate;
 //         smax, k* = max/argmax sim;  L = (sim == smax);  P = softmax(t sim);  E = sum P log P
 //         loss partials: smax, E, sim[k^]
@@ -55,17 +55,6 @@ __device__ __forceinline__ float warp_sum(float v)
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// max with FIRST index on ties (torch.argmax / max(dim) convention used by the oracle)
-__device__ __forceinline__ void warp_argmax(float& v, int& idx)
-{
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-}
-
 __global__ void __launch_bounds__(128) k_lut_normalize(int K, int D, const float* __restrict__ lut,
                                                        float* __restrict__ lut1, float* __restrict__ norm)
 {
@@ -130,79 +119,10 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane)
 }
 __device__ __forceinline__ int dx_channel(int lane, int n) { return n == 32 ? lane : (lane >> 1); }
 
-// Both logit-side kernels: a warp owns PXB pixels at a time, lane l owns codebook rows k = l, l + 32, ... (KI per lane).
+// The logit-side row kernel: a warp owns PXB pixels at a time, lane l owns codebook rows k = l, l + 32, ... (KI per lane).
 // A weight row (S floats, LDS.128) is loaded once and used for all PXB pixels -- the one-pixel-at-a-time kernel of
 // round 1 issued one LDS.128 per 4 FMAs and was bound by the shared-memory pipe (l1tex 90 %), not by the FMAs.
 template <int NS4, int KI> struct PixBlock { static constexpr int PXB = (NS4 <= 4 && KI <= 10) ? 4 : 2; };
-
-// k^ = argmax_k (W x + b)_k per pixel (first maximum, like torch.argmax): the codebook row train.py:156 looks up.
-// Weights staged once per CTA (rows padded with bias -inf).
-template <int NS4, int KI>
-__global__ void __launch_bounds__(ROWS_THREADS, 2)
-k_semloss_zarg(int64_t N, int S, int K, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
-               const float* __restrict__ W, const float* __restrict__ bias, int* __restrict__ zarg)
-{
-    constexpr int SP = 4 * NS4, WS = SP + 4, KP = 32 * KI, PXB = PixBlock<NS4, KI>::PXB;
-    extern __shared__ float4 smem4[];
-    float* s_w = reinterpret_cast<float*>(smem4);               // [KP][WS]
-    float* s_b = s_w + (size_t)KP * WS;                         // [KP]
-    float* s_x = s_b + KP;                                      // [8 warps][2][PXB][SP]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < KP * SP; i += ROWS_THREADS) {
-        const int k = i / SP, c = i % SP;
-        s_w[k * WS + c] = (k < K && c < S) ? W[(size_t)k * S + c] : 0.f;
-    }
-    for (int i = tid; i < KP; i += ROWS_THREADS) s_b[i] = i < K ? (bias ? bias[i] : 0.f) : -INFINITY;
-    __syncthreads();
-    const int64_t ngroups = (N + PXB - 1) / PXB;
-    const int64_t nwarps = (int64_t)gridDim.x * (ROWS_THREADS / 32);
-    int par = 0;
-    for (int64_t gq = (int64_t)blockIdx.x * (ROWS_THREADS / 32) + warp; gq < ngroups; gq += nwarps, par ^= 1) {
-        const int64_t p0 = gq * PXB;
-        float* xg = s_x + (warp * 2 + par) * PXB * SP;          // double-buffered: one __syncwarp per group
-        for (int i = lane; i < PXB * SP; i += 32) {
-            const int px = i / SP, c = i % SP;
-            xg[i] = (c < S && p0 + px < N) ? x[(p0 + px) * xs_n + c * xs_c] : 0.f;
-        }
-        __syncwarp();
-        float xs[PXB][SP];
-#pragma unroll
-        for (int px = 0; px < PXB; ++px)
-#pragma unroll
-            for (int q = 0; q < NS4; ++q) {
-                const float4 v = reinterpret_cast<const float4*>(xg + px * SP)[q];
-                xs[px][4 * q] = v.x; xs[px][4 * q + 1] = v.y; xs[px][4 * q + 2] = v.z; xs[px][4 * q + 3] = v.w;
-            }
-        float zmax[PXB];
-        int za[PXB];
-#pragma unroll
-        for (int px = 0; px < PXB; ++px) { zmax[px] = -INFINITY; za[px] = 0; }
-#pragma unroll
-        for (int i = 0; i < KI; ++i) {
-            const int k = lane + 32 * i;
-            float w[SP];
-#pragma unroll
-            for (int q = 0; q < NS4; ++q) {
-                const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * WS + 4 * q);
-                w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
-            }
-            const float bk = s_b[k];
-#pragma unroll
-            for (int px = 0; px < PXB; ++px) {
-                float a = 0.f;
-#pragma unroll
-                for (int c = 0; c < SP; ++c) a = fmaf(xs[px][c], w[c], a);
-                a += bk;
-                if (a > zmax[px]) { zmax[px] = a; za[px] = k; }      // ascending k: first maximum wins
-            }
-        }
-#pragma unroll
-        for (int px = 0; px < PXB; ++px) {
-            warp_argmax(zmax[px], za[px]);
-            if (lane == 0 && p0 + px < N) zarg[p0 + px] = za[px];
-        }
-    }
-}
 
 // One pass per pixel over its logit row; see the header of this file.
 // Phase A: PXB pixels at a time per warp (see above); the label bits of the next group are prefetched.
@@ -581,14 +501,14 @@ cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const G
     constexpr int KP = 32 * KI;                                 // padded codebook rows (see the kernel)
     const int sms = device_sms();
     {
-        const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + 16 * PixBlock<NS4, KI>::PXB * SP);
-        auto kern = k_semloss_zarg<NS4, KI>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // arg-max of the logits on the tensor cores (k_zarg_tc): operands = W, b and one 128-pixel tile of x
+        const int KPz = ((a.S + 1 + 7) / 8) * 8;
+        const size_t smem = (size_t)2 * (g.NP / 8) * (KPz / 4) * 128 + (size_t)2 * 16 * (KPz / 4) * 128;
+        cudaError_t e = cudaFuncSetAttribute(tc5::k_zarg_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int64_t grid = (a.N + 8 * PixBlock<NS4, KI>::PXB - 1) / (8 * PixBlock<NS4, KI>::PXB);
-        if (grid > (int64_t)sms * 2) grid = (int64_t)sms * 2;
-        kern<<<(unsigned)grid, ROWS_THREADS, smem, st>>>(a.N, a.S, a.K, a.x, a.x_stride_n, a.x_stride_c, a.mlp_weight,
-                                                        a.mlp_bias, w.zarg);
+        const unsigned grid = (unsigned)(g.ntiles < sms ? g.ntiles : sms);
+        tc5::k_zarg_tc<<<grid, tc5::THREADS, smem, st>>>(a.N, a.S, a.K, g.NP, KPz, a.x, a.x_stride_n, a.x_stride_c,
+                                                         a.mlp_weight, a.mlp_bias, w.zarg);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -628,6 +628,143 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_zarg_tc: k^ = argmax_k (W x + b)_k per pixel (first maximum, like torch.argmax) -- the codebook row train.py:156
+// looks up.  The S -> K projection of 128 pixels is one batch of tcgen05 MMAs (3 x TF32, the bias folded in as one
+// more reduction column: x carries a 1 there, padded codebook rows a -3e38), the arg-max is one sweep over the
+// accumulator row out of tensor memory; thread (row = t & 127, part = t >> 7) owns a pixel and half of the columns,
+// ascending with a strict > so that the first maximum wins, part 0 winning ties against part 1.
+// Operands (small: KP = S + 1 rounded up to 8 reduction elements) use the no-swizzle K-major layout of the mask kernel:
+// element (row r, k) at (r / 8) SBO + (k / 4) 128 + (r % 8) 16 + (k % 4) 4, SBO = (KP / 4) 128.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t smem_desc_plain(uint32_t saddr, int sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address
+    d |= (uint64_t)(128 >> 4) << 16;                        // leading byte offset: the two 16-byte K pieces of a k-step
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;             // stride byte offset (8-row groups)
+    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (sm_100)
+    return d;                                               // SWIZZLE_NONE
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
+          const float* __restrict__ W, const float* __restrict__ bias, int* __restrict__ zarg)
+{
+    extern __shared__ __align__(128) uint8_t smem_z[];
+    const int SBO = (KP / 4) * 128;
+    const int w_bytes = (NP / 8) * SBO, x_bytes = 16 * SBO;
+    uint8_t* sWhi = smem_z;
+    uint8_t* sWlo = sWhi + w_bytes;
+    uint8_t* sXhi = sWlo + w_bytes;
+    uint8_t* sXlo = sXhi + x_bytes;
+    __shared__ __align__(8) uint64_t s_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_pv[128];
+    __shared__ int s_pi[128];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, part = tid >> 7;
+    const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
+    auto elem_off = [SBO](int r, int k) { return (r >> 3) * SBO + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4; };
+
+    for (int i = tid; i < NP * KP; i += THREADS) {           // projection + bias column; padded rows can never win
+        const int r = i / KP, k = i - r * KP;
+        float v = 0.f;
+        if (r < K) v = k < S ? W[(size_t)r * S + k] : (k == S ? (bias ? bias[r] : 0.f) : 0.f);
+        else if (k == S) v = -3.0e38f;
+        const uint32_t hi = __float_as_uint(v) & 0xffffe000u;
+        *reinterpret_cast<uint32_t*>(sWhi + elem_off(r, k)) = hi;
+        *reinterpret_cast<float*>(sWlo + elem_off(r, k)) = v - __uint_as_float(hi);
+    }
+    if (tid == 0) {
+        mbar_init(&s_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+
+    const int64_t n_tiles = (N + 127) / 128;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr int HALF_K = 20;                               // KP <= 40: a thread stages channels [20 part, 20 part + 20) of its pixel
+    float xv[HALF_K];
+    auto load_x = [&](int64_t tile) {
+        const int64_t n = tile * 128 + row;
+        const float* px = x + n * xs_n;
+#pragma unroll
+        for (int j = 0; j < HALF_K; ++j) {
+            const int k = HALF_K * part + j;
+            xv[j] = (k < S && n < N) ? __ldg(px + k * xs_c) : (k == S ? 1.f : 0.f);
+        }
+    };
+    if (my_tiles > 0) load_x(blockIdx.x);
+    int64_t tile = blockIdx.x;
+    for (int64_t it = 0; it < my_tiles; ++it, tile += gridDim.x) {
+        // operands of this tile (the previous tile's MMAs have completed: every thread waited for them below)
+#pragma unroll
+        for (int j4 = 0; j4 < HALF_K; j4 += 4) {
+            const int k4 = HALF_K * part + j4;
+            if (k4 < KP) store_split(smem_u32(sXhi), smem_u32(sXlo), (uint32_t)elem_off(row, k4), xv[j4], xv[j4 + 1], xv[j4 + 2], xv[j4 + 3], true);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;");  // (the previous tile's tcgen05.ld of every thread)
+        __syncthreads();
+        if (it + 1 < my_tiles) load_x(tile + gridDim.x);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int nn = half == 0 ? N0 : N1;
+                if (nn == 0) continue;
+                const uint32_t idesc = instr_desc(128, nn);
+                const uint32_t row0 = half == 0 ? 0u : (uint32_t)((N0 / 8) * SBO);
+                const uint32_t d = tmem + (half == 0 ? 0u : (uint32_t)N0);
+                uint32_t acc = 0u;
+                for (int term = 0; term < 3; ++term) {      // small terms first: X_lo W_hi, X_hi W_lo, X_hi W_hi
+                    const uint32_t a = smem_u32(term == 0 ? sXlo : sXhi), b = smem_u32(term == 1 ? sWlo : sWhi) + row0;
+                    for (int ks = 0; ks < KP / 8; ++ks) {
+                        mma_tf32(d, smem_desc_plain(a + ks * 256, SBO), smem_desc_plain(b + ks * 256, SBO), idesc, acc);
+                        acc = 1u;
+                    }
+                }
+            }
+            commit(smem_u32(&s_acc));
+        }
+        wait(smem_u32(&s_acc), (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+
+        const int C0 = min(NP, 32 * ((NP + 63) / 64));
+        const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        float bv0 = -INFINITY, bv1 = -INFINITY;
+        int bi0 = 0, bi1 = 0;
+        for_blocks(lane_base, cbeg, cend, NP, [&](const uint32_t (&v)[32], int c0, int cnt, bool) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                if (j < cnt) {                               // cnt is 16 or 32: whole pairs
+                    const float r0 = __uint_as_float(v[j]), r1 = __uint_as_float(v[j + 1]);
+                    if (r0 > bv0) { bv0 = r0; bi0 = c0 + j; }
+                    if (r1 > bv1) { bv1 = r1; bi1 = c0 + j + 1; }
+                }
+            }
+        });
+        if (bv1 > bv0 || (bv1 == bv0 && bi1 < bi0)) { bv0 = bv1; bi0 = bi1; }     // first maximum
+        if (part == 1) { s_pv[row] = bv0; s_pi[row] = bi0; }
+        __syncthreads();
+        const int64_t n = tile * 128 + row;
+        if (part == 0 && n < N) zarg[n] = s_pv[row] > bv0 ? s_pi[row] : bi0;
+        // (s_pv / s_pi are rewritten only after the next tile's block barrier)
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // The codebook operand of k_sim_tc: lut1 split once into TF32 hi / lo images, chunk by chunk, already in the shared-
 // memory layout (rows >= K and columns >= D are zeros) so that a stage is one bulk copy per image.
 __global__ void __launch_bounds__(256) k_build_wimg(int K, int D, int NP, int KC, int nchunks,

@@ -20,7 +20,7 @@
  * lives in tensor memory and the only [N,K] array in HBM is its gradient:
  *
  *     1. k_lut_normalize, k_build_wimg                        (tiny: codebook rows, their TF32 hi / lo operand images)
- *     2. k_semloss_zarg: argmax of the MLP logits             (reads x)
+ *     2. k_zarg_tc: argmax of the MLP logits on tcgen05      (reads x)
  *     3. k_sim_tc: sim = gt/|gt| @ lut1^T on tcgen05 (accumulators in TMEM), then per pixel out of tensor memory:
  *        row max / arg-max / label bits, entropy, the similarity-side loss terms and d/dsim (written once)
  *     4. k_semloss_rows: per pixel, ONE pass: MLP logits + softmax, (P' - L)^2, d/dlogits -> dL/dsem_feature,
