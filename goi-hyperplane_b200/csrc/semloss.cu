@@ -514,6 +514,19 @@ cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const G
     }
     cudaError_t e = launch_sim(a, w, g, st);
     if (e != cudaSuccess) return e;
+    if (a.S <= 16 && a.K <= 320) {
+        // the logit side with every contraction on tensor cores (k_logit_tc); wider shapes keep the FMA kernel below
+        const int KPz = ((a.S + 1 + 7) / 8) * 8, ntn = a.S <= 8 ? 1 : 2, sps = 8 * ntn + 8;
+        const size_t smem = (size_t)2 * (g.NP / 8) * (KPz / 4) * 128 + (size_t)2 * 16 * (KPz / 4) * 128 +
+                            sizeof(float) * ((size_t)320 * sps * 2 + 128 * sps + 2 * 128 * 36);
+        auto kl = ntn == 1 ? tc5::k_logit_tc<1> : tc5::k_logit_tc<2>;
+        e = cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)(g.ntiles < sms ? g.ntiles : sms);
+        kl<<<grid, tc5::THREADS, smem, st>>>(a.N, a.S, a.K, g.NP, KPz, a.x, a.x_stride_n, a.x_stride_c, w.lmask, g.Npad,
+                                             a.mlp_weight, a.mlp_bias, a.dL_dx, a.dL_dmlp_weight, a.dL_dmlp_bias, &w.acc->lab);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(float) * ((size_t)KP * (SP + 4) + KP + PB * SP + (size_t)PB * KP);
     auto kern = k_semloss_rows<NS4, KI>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

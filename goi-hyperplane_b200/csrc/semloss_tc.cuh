@@ -765,6 +765,327 @@ k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_logit_tc: the logit side of the loss for S <= 16 channels and K <= 320 codebook rows (train.py:143-144, 154 and
+// their backward) with every contraction on tensor cores:
+//   z = W x + b for 128 pixels          tcgen05 MMAs into TMEM (as k_zarg_tc)
+//   row pass out of TMEM, thread (row = t & 127, part = t >> 7) = (pixel, half of the 32-column blocks):
+//     sweep 1  row maximum;  sweep 2  e = exp(z - max): sum e, sum e^2, sum of e over the label bits -- lab = sum (P' - L)^2
+//     and dot = sum P' g follow from these three sums;  sweep 3  dz = P' (cl (P' - L) - dot), one 32-column block per
+//     part at a time into a shared-memory block buffer [pixel][32 codebook rows]
+//   per block pair, all eight warps (warp-level mma.sync m16n8k8, TF32 hi + lo split = fp32-accurate):
+//     dx[16 pixels of the warp x S] += dz_block W_block          (accumulators in registers for the whole tile)
+//     dW_block[32 rows x S] (+ db through a ones column) = dz_block^T x over a quarter of the pixels, flushed into a
+//     shared-memory dW / db accumulator with red.shared
+// The FMA kernel it replaces (k_semloss_rows, still used for S > 16 or K > 320) was bound by dependent LDS -> FMA chains.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_sync_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo)
+{
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+template <int NTN>                                          // 8-channel tiles: 1 (S <= 8) or 2 (S <= 16)
+__global__ void __launch_bounds__(THREADS, 1)
+k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
+           const uint32_t* __restrict__ lmask, int64_t Npad, const float* __restrict__ W,
+           const float* __restrict__ bias, float* __restrict__ dL_dx, float* __restrict__ dW, float* __restrict__ db,
+           double* __restrict__ lab_out)
+{
+    constexpr int SPS = 8 * NTN + 8;                        // row stride (floats) of s_x, s_wf and s_dw: 16 or 24 -> conflict-free B fragments
+    constexpr int DS = 36;                                  // row stride of a dz block: conflict-free A fragments of dx, 16-byte aligned rows
+    constexpr int KPAD = 320;                               // codebook rows padded to ten 32-row blocks
+    extern __shared__ __align__(128) uint8_t smem_l[];
+    const int SBO = (KP / 4) * 128;
+    const int w_bytes = (NP / 8) * SBO, x_bytes = 16 * SBO;
+    uint8_t* sWhi = smem_l;
+    uint8_t* sWlo = sWhi + w_bytes;
+    uint8_t* sXhi = sWlo + w_bytes;
+    uint8_t* sXlo = sXhi + x_bytes;
+    float* s_wf = reinterpret_cast<float*>(sXlo + x_bytes);    // [KPAD][SPS]   W[k][c] (zeros outside K x S): B operand of dx
+    float* s_x = s_wf + KPAD * SPS;                            // [128][SPS]    features of the tile: B operand of dW
+    float* s_dz = s_x + 128 * SPS;                             // [2][128][DS]  one dz block per part
+    float* s_dw = s_dz + 2 * 128 * DS;                         // [KPAD][SPS]   dW (columns < S) and db (column 8 NTN) of this CTA
+    __shared__ __align__(8) uint64_t s_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_e0[2][128], s_e1[2][128], s_e2[2][128], s_e4[2][128];
+    __shared__ int s_e3[2][128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int row = tid & 127, part = tid >> 7;
+    const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
+    const int NB = (NP + 31) / 32, NB0 = (NB + 1) / 2;      // 32-column blocks; part 0 owns [0, NB0), part 1 [NB0, NB)
+    auto elem_off = [SBO](int r, int k) { return (r >> 3) * SBO + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4; };
+
+    for (int i = tid; i < NP * KP; i += THREADS) {           // logits operand: projection + bias column; padded rows -> -3e38
+        const int r = i / KP, k = i - r * KP;
+        float v = 0.f;
+        if (r < K) v = k < S ? W[(size_t)r * S + k] : (k == S ? (bias ? bias[r] : 0.f) : 0.f);
+        else if (k == S) v = -3.0e38f;
+        const uint32_t hi = __float_as_uint(v) & 0xffffe000u;
+        *reinterpret_cast<uint32_t*>(sWhi + elem_off(r, k)) = hi;
+        *reinterpret_cast<float*>(sWlo + elem_off(r, k)) = v - __uint_as_float(hi);
+    }
+    for (int i = tid; i < KPAD * SPS; i += THREADS) {
+        const int k = i / SPS, c = i - k * SPS;
+        s_wf[i] = (k < K && c < S) ? W[(size_t)k * S + c] : 0.f;
+        s_dw[i] = 0.f;
+    }
+    for (int i = tid; i < 128 * SPS; i += THREADS) s_x[i] = 0.f;
+    if (tid == 0) {
+        mbar_init(&s_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+
+    const int64_t n_tiles = (N + 127) / 128;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const float cl = 100.0f / ((float)N * (float)K);        // d(50 * MSE)/d(P') = 2 * 50 / (N K) * (P' - L)
+    constexpr float LOG2E = 1.4426950408889634f;
+    constexpr int HALF_K = 20;                               // KP <= 24 here; part 0 stages channels 0 .. 19, part 1 the rest
+    float xv[HALF_K];
+    auto load_x = [&](int64_t tile) {
+        const int64_t n = tile * 128 + row;
+        const float* px = x + n * xs_n;
+#pragma unroll
+        for (int j = 0; j < HALF_K; ++j) {
+            const int k = HALF_K * part + j;
+            xv[j] = (k < S && n < N) ? __ldg(px + k * xs_c) : (k == S ? 1.f : 0.f);
+        }
+    };
+    if (my_tiles > 0) load_x(blockIdx.x);
+    double l_lab = 0.0;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+
+    int64_t tile = blockIdx.x;
+    for (int64_t it = 0; it < my_tiles; ++it, tile += gridDim.x) {
+        const int64_t n = tile * 128 + row;
+        const bool rv = n < N;
+        // ---- operands of this tile: TF32 images for the logits, plain fp32 rows for the dW product
+#pragma unroll
+        for (int j4 = 0; j4 < HALF_K; j4 += 4) {
+            const int k4 = HALF_K * part + j4;
+            if (k4 < KP) store_split(smem_u32(sXhi), smem_u32(sXlo), (uint32_t)elem_off(row, k4), xv[j4], xv[j4 + 1], xv[j4 + 2], xv[j4 + 3], true);
+        }
+        if (part == 0) {
+#pragma unroll
+            for (int c = 0; c < 8 * NTN; ++c) s_x[row * SPS + c] = c < S ? xv[c] : 0.f;
+        }
+        // label bits of this thread's blocks (bit j of word i = column 32 (first block + i) + j)
+        uint32_t lw[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int b = (part ? NB0 : 0) + i;
+            lw[i] = (rv && i < NB0 && b < NB) ? __ldg(lmask + (size_t)b * Npad + (size_t)n) : 0u;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (it + 1 < my_tiles) load_x(tile + gridDim.x);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int nn = half == 0 ? N0 : N1;
+                if (nn == 0) continue;
+                const uint32_t idesc = instr_desc(128, nn);
+                const uint32_t row0 = half == 0 ? 0u : (uint32_t)((N0 / 8) * SBO);
+                const uint32_t d = tmem + (half == 0 ? 0u : (uint32_t)N0);
+                uint32_t acc = 0u;
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t a = smem_u32(term == 0 ? sXlo : sXhi), b = smem_u32(term == 1 ? sWlo : sWhi) + row0;
+                    for (int ks = 0; ks < KP / 8; ++ks) {
+                        mma_tf32(d, smem_desc_plain(a + ks * 256, SBO), smem_desc_plain(b + ks * 256, SBO), idesc, acc);
+                        acc = 1u;
+                    }
+                }
+            }
+            commit(smem_u32(&s_acc));
+        }
+        wait(smem_u32(&s_acc), (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+
+        const int bfirst = part ? NB0 : 0, bend = part ? NB : NB0;
+        uint32_t v[32];
+        // ---- sweep 1: row maximum
+        float zmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int b = bfirst + i;
+            if (b < bend) {
+                const int c0 = 32 * b, cnt = min(32, NP - c0);
+                ld_cols(lane_base + (uint32_t)c0, cnt, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < cnt) zmax = fmaxf(zmax, __uint_as_float(v[j]));
+            }
+        }
+        s_e0[part][row] = zmax;
+        __syncthreads();
+        zmax = fmaxf(s_e0[0][row], s_e0[1][row]);
+        const float zoff = -zmax * LOG2E;
+        // ---- sweep 2: e = exp(z - max): sum e, sum e^2, sum over the label bits, number of label bits
+        float es = 0.f, e2 = 0.f, eL = 0.f;
+        int nL = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int b = bfirst + i;
+            if (b < bend) {
+                const int c0 = 32 * b, cnt = min(32, NP - c0);
+                ld_cols(lane_base + (uint32_t)c0, cnt, v);
+                const uint32_t bits = lw[i];
+                nL += __popc(bits);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < cnt) {
+                        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, zoff));      // padded rows: 2^-huge = 0
+                        es += e;
+                        e2 = fmaf(e, e, e2);
+                        eL += ((bits >> j) & 1u) ? e : 0.f;
+                    }
+            }
+        }
+        s_e1[part][row] = es; s_e2[part][row] = e2; s_e4[part][row] = eL; s_e3[part][row] = nL;
+        __syncthreads();
+        es = s_e1[0][row] + s_e1[1][row];
+        e2 = s_e2[0][row] + s_e2[1][row];
+        eL = s_e4[0][row] + s_e4[1][row];
+        nL = s_e3[0][row] + s_e3[1][row];
+        const float zinv = 1.f / es;
+        const float sP2 = e2 * zinv * zinv, sPL = eL * zinv;      // sum P'^2, sum of P' over the label bits
+        const float dot = cl * (sP2 - sPL);                       // sum P' g, g = cl (P' - L)
+        if (rv && part == 0) l_lab += (double)(sP2 - 2.f * sPL + (float)nL);      // sum (P' - L)^2
+
+        // ---- sweep 3 + the two products, one 32-column block per part at a time
+        float accx[NTN][4];
+#pragma unroll
+        for (int nt = 0; nt < NTN; ++nt) { accx[nt][0] = accx[nt][1] = accx[nt][2] = accx[nt][3] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i >= NB0) break;
+            const int b = bfirst + i;
+            float* dzrow = s_dz + ((size_t)part * 128 + row) * DS;
+            if (b < bend) {
+                const int c0 = 32 * b, cnt = min(32, NP - c0);
+                ld_cols(lane_base + (uint32_t)c0, cnt, v);
+                const uint32_t bits = lw[i];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float d4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float Pz = ex2_approx(fmaf(__uint_as_float(v[j + q]), LOG2E, zoff)) * zinv;
+                        const float g = fmaf(cl, Pz - (((bits >> (j + q)) & 1u) ? 1.f : 0.f), -dot);
+                        d4[q] = (j + q < cnt && rv) ? Pz * g : 0.f;      // padded rows: P' = 0
+                    }
+                    *reinterpret_cast<float4*>(dzrow + j) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dzrow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                const int bb = (blk ? NB0 : 0) + i;          // global block index of this buffer
+                if (bb >= (blk ? NB : NB0)) continue;
+                const float* dzb = s_dz + (size_t)blk * 128 * DS;
+                // dx: this warp's 16 pixels x the block's 32 codebook rows (4 k-steps)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const float* ap = dzb + (16 * warp + gid) * DS + 8 * ks + tig;
+                    uint32_t ah[4], al[4];
+                    split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8 * DS], ah[1], al[1]);
+                    split_tf32(ap[4], ah[2], al[2]); split_tf32(ap[8 * DS + 4], ah[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < NTN; ++nt) {
+                        const float* bp = s_wf + (32 * bb + 8 * ks + tig) * SPS + 8 * nt + gid;
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_tf32(bp[0], bh0, bl0); split_tf32(bp[4 * SPS], bh1, bl1);
+                        mma_sync_tf32(accx[nt], al, bh0, bh1);
+                        mma_sync_tf32(accx[nt], ah, bl0, bl1);
+                        mma_sync_tf32(accx[nt], ah, bh0, bh1);
+                    }
+                }
+                // dW / db: 16 of the block's rows (mt) x a quarter of the pixels (kq): 4 k-steps, then flush
+                {
+                    const int mt = warp & 1, kq = warp >> 1;
+                    float accd[NTN + 1][4];
+#pragma unroll
+                    for (int nt = 0; nt <= NTN; ++nt) { accd[nt][0] = accd[nt][1] = accd[nt][2] = accd[nt][3] = 0.f; }
+                    const uint32_t one = gid == 0 ? 0x3f800000u : 0u;      // ones tile: column 0 = 1 -> db
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const int px0 = 32 * kq + 8 * ks;
+                        const float* ap = dzb + (px0 + tig) * DS + 16 * mt + gid;      // A[row = codebook row][k = pixel]
+                        uint32_t ah[4], al[4];
+                        split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8], ah[1], al[1]);
+                        split_tf32(ap[4 * DS], ah[2], al[2]); split_tf32(ap[4 * DS + 8], ah[3], al[3]);
+#pragma unroll
+                        for (int nt = 0; nt < NTN; ++nt) {
+                            const float* bp = s_x + (px0 + tig) * SPS + 8 * nt + gid;
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(bp[0], bh0, bl0); split_tf32(bp[4 * SPS], bh1, bl1);
+                            mma_sync_tf32(accd[nt], al, bh0, bh1);
+                            mma_sync_tf32(accd[nt], ah, bl0, bl1);
+                            mma_sync_tf32(accd[nt], ah, bh0, bh1);
+                        }
+                        mma_sync_tf32(accd[NTN], al, one, one);
+                        mma_sync_tf32(accd[NTN], ah, one, one);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float* drow = s_dw + (32 * bb + 16 * mt + gid + 8 * (e >> 1)) * SPS;
+#pragma unroll
+                        for (int nt = 0; nt < NTN; ++nt) atomicAdd(drow + 8 * nt + 2 * tig + (e & 1), accd[nt][e]);
+                        if (tig == 0 && (e & 1) == 0) atomicAdd(drow + 8 * NTN, accd[NTN][e]);
+                    }
+                }
+            }
+            __syncthreads();                                // the block buffers are rewritten by the next iteration
+        }
+        // ---- dx of the tile: C fragment rows = pixels 16 warp + gid (+ 8), columns = channels 8 nt + 2 tig (+ 1)
+        if (dL_dx) {
+#pragma unroll
+            for (int nt = 0; nt < NTN; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t p = tile * 128 + 16 * warp + gid + 8 * (e >> 1);
+                    const int c = 8 * nt + 2 * tig + (e & 1);
+                    if (p < N && c < S) dL_dx[p * xs_n + c * xs_c] = accx[nt][e];
+                }
+        }
+    }
+
+    // ---- this CTA's dW / db and loss partial sum
+    __syncthreads();
+    if (dW) {
+        for (int i = tid; i < K * (S + 1); i += THREADS) {
+            const int k = i / (S + 1), c = i - k * (S + 1);
+            if (c < S) atomicAdd(dW + (size_t)k * S + c, s_dw[k * SPS + c]);
+            else if (db) atomicAdd(db + k, s_dw[k * SPS + 8 * NTN]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) l_lab += __shfl_xor_sync(0xffffffffu, l_lab, o);
+    if (lane == 0 && my_tiles > 0) atomicAdd(lab_out, l_lab);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // The codebook operand of k_sim_tc: lut1 split once into TF32 hi / lo images, chunk by chunk, already in the shared-
 // memory layout (rows >= K and columns >= D are zeros) so that a stage is one bulk copy per image.
 __global__ void __launch_bounds__(256) k_build_wimg(int K, int D, int NP, int KC, int nchunks,
