@@ -518,7 +518,7 @@ cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const G
         // the logit side with every contraction on tensor cores (k_logit_tc); wider shapes keep the FMA kernel below
         const int KPz = ((a.S + 1 + 7) / 8) * 8, ntn = a.S <= 8 ? 1 : 2, sps = 8 * ntn + 8;
         const size_t smem = (size_t)2 * (g.NP / 8) * (KPz / 4) * 128 + (size_t)2 * 16 * (KPz / 4) * 128 +
-                            sizeof(float) * ((size_t)320 * sps * 2 + 128 * sps + 2 * 128 * 36);
+                            sizeof(float) * ((size_t)320 * sps * 3 + 128 * sps + 2 * 128 * 36);
         auto kl = ntn == 1 ? tc5::k_logit_tc<1> : tc5::k_logit_tc<2>;
         e = cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

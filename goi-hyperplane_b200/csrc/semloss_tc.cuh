@@ -808,8 +808,9 @@ k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x,
     uint8_t* sWlo = sWhi + w_bytes;
     uint8_t* sXhi = sWlo + w_bytes;
     uint8_t* sXlo = sXhi + x_bytes;
-    float* s_wf = reinterpret_cast<float*>(sXlo + x_bytes);    // [KPAD][SPS]   W[k][c] (zeros outside K x S): B operand of dx
-    float* s_x = s_wf + KPAD * SPS;                            // [128][SPS]    features of the tile: B operand of dW
+    uint32_t* s_wfh = reinterpret_cast<uint32_t*>(sXlo + x_bytes);   // [KPAD][SPS]   W[k][c] (zeros outside K x S), TF32 hi bits: B operand of dx
+    uint32_t* s_wfl = s_wfh + KPAD * SPS;                            // [KPAD][SPS]   ... lo parts
+    float* s_x = reinterpret_cast<float*>(s_wfl + KPAD * SPS);       // [128][SPS]    features of the tile: B operand of dW
     float* s_dz = s_x + 128 * SPS;                             // [2][128][DS]  one dz block per part
     float* s_dw = s_dz + 2 * 128 * DS;                         // [KPAD][SPS]   dW (columns < S) and db (column 8 NTN) of this CTA
     __shared__ __align__(8) uint64_t s_acc;
@@ -833,7 +834,7 @@ k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x,
     }
     for (int i = tid; i < KPAD * SPS; i += THREADS) {
         const int k = i / SPS, c = i - k * SPS;
-        s_wf[i] = (k < K && c < S) ? W[(size_t)k * S + c] : 0.f;
+        split_tf32((k < K && c < S) ? W[(size_t)k * S + c] : 0.f, s_wfh[i], s_wfl[i]);
         s_dw[i] = 0.f;
     }
     for (int i = tid; i < 128 * SPS; i += THREADS) s_x[i] = 0.f;
@@ -927,9 +928,13 @@ k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x,
             if (b < bend) {
                 const int c0 = 32 * b, cnt = min(32, NP - c0);
                 ld_cols(lane_base + (uint32_t)c0, cnt, v);
+                if (cnt == 32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < cnt) zmax = fmaxf(zmax, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) zmax = fmaxf(zmax, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) zmax = fmaxf(zmax, __uint_as_float(v[j]));
+                }
             }
         }
         s_e0[part][row] = zmax;
@@ -947,14 +952,17 @@ k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x,
                 ld_cols(lane_base + (uint32_t)c0, cnt, v);
                 const uint32_t bits = lw[i];
                 nL += __popc(bits);
+                if (cnt < 32) {                             // a 16-column last block: the upper half reads as "very negative"
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < cnt) {
-                        const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, zoff));      // padded rows: 2^-huge = 0
-                        es += e;
-                        e2 = fmaf(e, e, e2);
-                        eL += ((bits >> j) & 1u) ? e : 0.f;
-                    }
+                    for (int j = 16; j < 32; ++j) v[j] = 0xff000000u;      // -1.7e38
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = ex2_approx(fmaf(__uint_as_float(v[j]), LOG2E, zoff));      // padded rows: 2^-huge = 0
+                    es += e;
+                    e2 = fmaf(e, e, e2);
+                    eL += ((bits >> j) & 1u) ? e : 0.f;
+                }
             }
         }
         s_e1[part][row] = es; s_e2[part][row] = e2; s_e4[part][row] = eL; s_e3[part][row] = nL;
@@ -981,14 +989,18 @@ k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x,
                 const int c0 = 32 * b, cnt = min(32, NP - c0);
                 ld_cols(lane_base + (uint32_t)c0, cnt, v);
                 const uint32_t bits = lw[i];
+                if (cnt < 32) {
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) v[j] = 0xff000000u;      // -1.7e38 -> P' = 0 -> dz = 0
+                }
+                const float zi = rv ? zinv : 0.f;           // pixels past the end: P' = 0 -> dz = 0
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float d4[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float Pz = ex2_approx(fmaf(__uint_as_float(v[j + q]), LOG2E, zoff)) * zinv;
-                        const float g = fmaf(cl, Pz - (((bits >> (j + q)) & 1u) ? 1.f : 0.f), -dot);
-                        d4[q] = (j + q < cnt && rv) ? Pz * g : 0.f;      // padded rows: P' = 0
+                        const float Pz = ex2_approx(fmaf(__uint_as_float(v[j + q]), LOG2E, zoff)) * zi;
+                        d4[q] = Pz * fmaf(cl, Pz - (((bits >> (j + q)) & 1u) ? 1.f : 0.f), -dot);      // padded rows: P' = 0
                     }
                     *reinterpret_cast<float4*>(dzrow + j) = make_float4(d4[0], d4[1], d4[2], d4[3]);
                 }
@@ -1011,9 +1023,8 @@ k_logit_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x,
                     split_tf32(ap[4], ah[2], al[2]); split_tf32(ap[8 * DS + 4], ah[3], al[3]);
 #pragma unroll
                     for (int nt = 0; nt < NTN; ++nt) {
-                        const float* bp = s_wf + (32 * bb + 8 * ks + tig) * SPS + 8 * nt + gid;
-                        uint32_t bh0, bl0, bh1, bl1;
-                        split_tf32(bp[0], bh0, bl0); split_tf32(bp[4 * SPS], bh1, bl1);
+                        const int bo = (32 * bb + 8 * ks + tig) * SPS + 8 * nt + gid;
+                        const uint32_t bh0 = s_wfh[bo], bh1 = s_wfh[bo + 4 * SPS], bl0 = s_wfl[bo], bl1 = s_wfl[bo + 4 * SPS];
                         mma_sync_tf32(accx[nt], al, bh0, bh1);
                         mma_sync_tf32(accx[nt], ah, bl0, bl1);
                         mma_sync_tf32(accx[nt], ah, bh0, bh1);
