@@ -9,12 +9,12 @@
 //         loss partials: smax, E, sim[k^]
 //         dsim = -(1/N)([k=k*] + [k=k^]) - (0.3 t / N) P (log P - E)   -> dsimT (pre-scaled by 1/|gt|), label bits L
 //         reads gt once (4ND), writes dsimT (4NK) + L (N K / 8): sim itself never reaches HBM
-//     per pixel, one pass                         k_semloss_rows             reads x (4NS) + L
-//         z = W x + b;  P' = softmax(z);  loss partial sum (P'-L)^2
+//     per pixel                                   k_logit_tc (S <= 16, K <= 320; semloss_tc.cuh) | k_semloss_rows (FMA)
+//         z = W x + b;  P' = softmax(z);  loss partial sum (P'-L)^2                    reads x (4NS) + L
 //         dz = P' (g - P'.g), g = 100/(NK) (P'-L)          -> dL/dx = dz W, dL/dW += dz x^T, dL/db += dz
 //     dlut1 = dsim^T @ gt  accumulated in TMEM    k_dlut_tc (semloss_tc.cuh) reads dsimT + gt (per 128-wide slice)
 //     dlut = (dlut1 - (dlut1.lut1) lut1) / |lut|  k_lut_normalize_bwd
-// No library GEMM: both contractions are hand-written tcgen05 kernels.  HBM roofline: 4N(2D + 2K + 2S) bytes per slice
+// No library GEMM: every contraction is a hand-written tensor-core kernel.  HBM roofline: 4N(2D + 2K + 2S) bytes per slice
 // pair; the row kernel is FP32-FMA bound (3 x K x S FMA per pixel for logits, dx and dW) next to that.
 #include <cuda_runtime.h>
 #include <stdarg.h>

@@ -23,8 +23,8 @@
  *     2. k_zarg_tc: argmax of the MLP logits on tcgen05      (reads x)
  *     3. k_sim_tc: sim = gt/|gt| @ lut1^T on tcgen05 (accumulators in TMEM), then per pixel out of tensor memory:
  *        row max / arg-max / label bits, entropy, the similarity-side loss terms and d/dsim (written once)
- *     4. k_semloss_rows: per pixel, ONE pass: MLP logits + softmax, (P' - L)^2, d/dlogits -> dL/dsem_feature,
- *        dL/dW, dL/db
+ *     4. k_logit_tc (S <= 16, K <= 320; k_semloss_rows otherwise): MLP logits on tcgen05, softmax / (P' - L)^2 /
+ *        d/dlogits out of tensor memory, dL/dsem_feature, dL/dW, dL/db as warp-level tensor-core products
  *     5. k_dlut_tc: dlut1 = dsim^T @ gt on tcgen05           (accumulators in TMEM, split over the pixel axis)
  *     6. k_lut_normalize_bwd, k_semloss_finalize
  *
