@@ -85,8 +85,8 @@ def test_semloss_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
 
 
 def test_semloss_library_is_self_contained_and_uses_the_blackwell_tensor_cores():
-    """Row f2 without library GEMMs: libgoi_semloss.so must not depend on cuBLAS, and its two contractions must be the
-    hand-written tcgen05 kernels (SASS: UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UBLKCP = cp.async.bulk)."""
+    """Row f2 without library GEMMs: libgoi_semloss.so must not depend on cuBLAS, and its contractions must be the
+    hand-written tensor-core kernels (SASS: UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UBLKCP = cp.async.bulk)."""
     import shutil
     import subprocess
     from goi_b200 import semantic_loss as sl
@@ -99,9 +99,9 @@ def test_semloss_library_is_self_contained_and_uses_the_blackwell_tensor_cores()
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, check=True).stdout
-    for kernel in ("k_sim_tc", "k_dlut_tc"):
+    for kernel in ("k_sim_tc", "k_dlut_tc", "k_zarg_tc", "k_logit_tc"):
         assert kernel in sass, kernel
-    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "HMMA"):      # tcgen05.mma, tcgen05.ld, cp.async.bulk, mma.sync
         assert mnemonic in sass, mnemonic
 
 
