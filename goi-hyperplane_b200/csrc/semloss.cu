@@ -504,10 +504,11 @@ cudaError_t launch_rows_t(const goi_semloss_args& a, const Workspace& w, const G
         // arg-max of the logits on the tensor cores (k_zarg_tc): operands = W, b and one 128-pixel tile of x
         const int KPz = ((a.S + 1 + 7) / 8) * 8;
         const size_t smem = (size_t)2 * (g.NP / 8) * (KPz / 4) * 128 + (size_t)2 * 16 * (KPz / 4) * 128;
-        cudaError_t e = cudaFuncSetAttribute(tc5::k_zarg_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        constexpr int ZPARTS = 4;                                // 16 warps: four column parts per pixel hide the sweep's latencies
+        cudaError_t e = cudaFuncSetAttribute(tc5::k_zarg_tc<ZPARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const unsigned grid = (unsigned)(g.ntiles < sms ? g.ntiles : sms);
-        tc5::k_zarg_tc<<<grid, tc5::THREADS, smem, st>>>(a.N, a.S, a.K, g.NP, KPz, a.x, a.x_stride_n, a.x_stride_c,
+        tc5::k_zarg_tc<ZPARTS><<<grid, 128 * ZPARTS, smem, st>>>(a.N, a.S, a.K, g.NP, KPz, a.x, a.x_stride_n, a.x_stride_c,
                                                          a.mlp_weight, a.mlp_bias, w.zarg);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -647,10 +647,12 @@ __device__ __forceinline__ uint64_t smem_desc_plain(uint32_t saddr, int sbo)
     return d;                                               // SWIZZLE_NONE
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NPARTS>                                       // column parts per pixel = warps per TMEM lane quarter (2 or 4)
+__global__ void __launch_bounds__(128 * NPARTS, 1)
 k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, int64_t xs_n, int64_t xs_c,
           const float* __restrict__ W, const float* __restrict__ bias, int* __restrict__ zarg)
 {
+    constexpr int NT = 128 * NPARTS;
     extern __shared__ __align__(128) uint8_t smem_z[];
     const int SBO = (KP / 4) * 128;
     const int w_bytes = (NP / 8) * SBO, x_bytes = 16 * SBO;
@@ -660,14 +662,14 @@ k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, 
     uint8_t* sXlo = sXhi + x_bytes;
     __shared__ __align__(8) uint64_t s_acc;
     __shared__ uint32_t s_tmem;
-    __shared__ float s_pv[128];
-    __shared__ int s_pi[128];
+    __shared__ float s_pv[NPARTS][128];
+    __shared__ int s_pi[NPARTS][128];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, part = tid >> 7;
     const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
     auto elem_off = [SBO](int r, int k) { return (r >> 3) * SBO + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4; };
 
-    for (int i = tid; i < NP * KP; i += THREADS) {           // projection + bias column; padded rows can never win
+    for (int i = tid; i < NP * KP; i += NT) {                // projection + bias column; padded rows can never win
         const int r = i / KP, k = i - r * KP;
         float v = 0.f;
         if (r < K) v = k < S ? W[(size_t)r * S + k] : (k == S ? (bias ? bias[r] : 0.f) : 0.f);
@@ -691,25 +693,29 @@ k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, 
 
     const int64_t n_tiles = (N + 127) / 128;
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    constexpr int HALF_K = 20;                               // KP <= 40: a thread stages channels [20 part, 20 part + 20) of its pixel
-    float xv[HALF_K];
+    constexpr int NPC = (10 + NPARTS - 1) / NPARTS;          // KP <= 40: ten 4-channel pieces; a thread stages pieces part, part + NPARTS, ..
+    float xv[4 * NPC];
     auto load_x = [&](int64_t tile) {
         const int64_t n = tile * 128 + row;
         const float* px = x + n * xs_n;
 #pragma unroll
-        for (int j = 0; j < HALF_K; ++j) {
-            const int k = HALF_K * part + j;
-            xv[j] = (k < S && n < N) ? __ldg(px + k * xs_c) : (k == S ? 1.f : 0.f);
-        }
+        for (int q = 0; q < NPC; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * (part + NPARTS * q) + j;
+                xv[4 * q + j] = (k < S && n < N) ? __ldg(px + k * xs_c) : (k == S ? 1.f : 0.f);
+            }
     };
     if (my_tiles > 0) load_x(blockIdx.x);
+    const int NB = (NP + 31) / 32;                          // 32-column blocks; part p sweeps blocks [NB p / NPARTS, NB (p + 1) / NPARTS)
+    const int cbeg = 32 * (NB * part / NPARTS), cend = min(NP, 32 * (NB * (part + 1) / NPARTS));
     int64_t tile = blockIdx.x;
     for (int64_t it = 0; it < my_tiles; ++it, tile += gridDim.x) {
         // operands of this tile (the previous tile's MMAs have completed: every thread waited for them below)
 #pragma unroll
-        for (int j4 = 0; j4 < HALF_K; j4 += 4) {
-            const int k4 = HALF_K * part + j4;
-            if (k4 < KP) store_split(smem_u32(sXhi), smem_u32(sXlo), (uint32_t)elem_off(row, k4), xv[j4], xv[j4 + 1], xv[j4 + 2], xv[j4 + 3], true);
+        for (int q = 0; q < NPC; ++q) {
+            const int k4 = 4 * (part + NPARTS * q);
+            if (k4 < KP) store_split(smem_u32(sXhi), smem_u32(sXlo), (uint32_t)elem_off(row, k4), xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3], true);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");  // (the previous tile's tcgen05.ld of every thread)
@@ -738,12 +744,13 @@ k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, 
         wait(smem_u32(&s_acc), (uint32_t)(it & 1));
         asm volatile("tcgen05.fence::after_thread_sync;");
 
-        const int C0 = min(NP, 32 * ((NP + 63) / 64));
-        const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
         const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         float bv0 = -INFINITY, bv1 = -INFINITY;
         int bi0 = 0, bi1 = 0;
-        for_blocks(lane_base, cbeg, cend, NP, [&](const uint32_t (&v)[32], int c0, int cnt, bool) {
+        uint32_t v[32];
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            const int cnt = min(32, cend - c0);
+            ld_cols(lane_base + (uint32_t)c0, cnt, v);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 if (j < cnt) {                               // cnt is 16 or 32: whole pairs
@@ -752,12 +759,18 @@ k_zarg_tc(int64_t N, int S, int K, int NP, int KP, const float* __restrict__ x, 
                     if (r1 > bv1) { bv1 = r1; bi1 = c0 + j + 1; }
                 }
             }
-        });
+        }
         if (bv1 > bv0 || (bv1 == bv0 && bi1 < bi0)) { bv0 = bv1; bi0 = bi1; }     // first maximum
-        if (part == 1) { s_pv[row] = bv0; s_pi[row] = bi0; }
+        s_pv[part][row] = bv0;
+        s_pi[part][row] = bi0;
         __syncthreads();
         const int64_t n = tile * 128 + row;
-        if (part == 0 && n < N) zarg[n] = s_pv[row] > bv0 ? s_pi[row] : bi0;
+        if (part == 0 && n < N) {
+#pragma unroll
+            for (int q = 1; q < NPARTS; ++q)                 // ascending parts, strict >: the first maximum wins
+                if (s_pv[q][row] > bv0) { bv0 = s_pv[q][row]; bi0 = s_pi[q][row]; }
+            zarg[n] = bi0;
+        }
         // (s_pv / s_pi are rewritten only after the next tile's block barrier)
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
