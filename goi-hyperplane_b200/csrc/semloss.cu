@@ -458,12 +458,14 @@ int device_sms()
 template <int KC, bool PLANAR>
 cudaError_t launch_sim_t(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
 {
-    auto kern = tc5::k_sim_tc<KC, PLANAR>;
+    constexpr int NT = 256;                                     // (512 threads = four column parts per pixel were measured slower:
+                                                                //  3.18 vs 2.39 ms -- 128 registers spill, half the warps idle while staging)
+    auto kern = tc5::k_sim_tc<KC, PLANAR, NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     const int sms = device_sms();
     const unsigned grid = (unsigned)(g.ntiles < sms ? g.ntiles : sms);
-    kern<<<grid, tc5::THREADS, g.smem, st>>>(a.N, a.D, a.K, g.NP, g.nchunks, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
+    kern<<<grid, NT, g.smem, st>>>(a.N, a.D, a.K, g.NP, g.nchunks, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
                                              a.anneal_t, a.gt, w.wimg, w.zarg, w.dsimT, w.lmask, g.Npad, &w.acc->sim, g.ns);
     return cudaGetLastError();
 }

@@ -131,6 +131,17 @@ __device__ __forceinline__ void for_blocks(uint32_t lane_base, int cbeg, int cen
         }
     }
 }
+// the same without the second register buffer (kernels with 16 warps hide the TMEM latency with other warps)
+template <typename F>
+__device__ __forceinline__ void for_blocks1(uint32_t lane_base, int cbeg, int cend, int K, F&& f)
+{
+    uint32_t v[32];
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        const int cnt = min(32, cend - c0);
+        ld_cols(lane_base + (uint32_t)c0, cnt, v);
+        f(v, c0, cnt, c0 + 32 <= K);
+    }
+}
 __device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -173,11 +184,11 @@ __device__ __forceinline__ float4 ld4(const float* p, int nvalid, bool vec)
 //                  16-byte vectors (coalesced: a warp reads 512 contiguous bytes per k) and transposed in registers.
 // Rows >= row_end and reduction elements >= k_end read as zeros.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KC, bool TRANS>
+template <int KC, bool TRANS, int NW = 8>                   // NW = warps of the CTA (8 or 16); the transposed mode uses the first 8
 struct RowTile {
     static constexpr int Q = KC / 4;                        // 16-byte pieces per row
     static constexpr int RPU = 32 / Q;                      // rows per warp instruction (direct mode)
-    static constexpr int NREG = TRANS ? 4 : Q / 2;          // float4 registers per thread
+    static constexpr int NREG = TRANS ? 4 : 4 * Q / NW;     // float4 registers per thread
     float4 v[NREG];
 
     // transposed mode: lane = hi * 8 + k4l * 2 + lo -> row quad 8 (warp % 4) + 2 hi + lo, piece 4 (warp / 4) + k4l.
@@ -202,7 +213,7 @@ struct RowTile {
             const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
             for (int it = 0; it < NREG; ++it) {
-                const int r = (it * 8 + w) * RPU + lane / Q, c = lane % Q;
+                const int r = (it * NW + w) * RPU + lane / Q, c = lane % Q;
                 const int64_t k = k0 + 4 * c;
                 v[it] = (row0 + r < row_end) ? ld4(src + (row0 + r) * ld + k, (int)min((int64_t)4, k_end - k), vec)
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,7 +238,7 @@ struct RowTile {
             const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
             for (int it = 0; it < NREG; ++it) {
-                const int r = (it * 8 + w) * RPU + lane / Q, c = lane % Q;
+                const int r = (it * NW + w) * RPU + lane / Q, c = lane % Q;
                 store_split(hi_base, lo_base, (uint32_t)piece_off(KC, r, c), v[it].x, v[it].y, v[it].z, v[it].w, want_lo);
                 ss[it] = fmaf(v[it].x, v[it].x, fmaf(v[it].y, v[it].y, fmaf(v[it].z, v[it].z, fmaf(v[it].w, v[it].w, ss[it]))));
             }
@@ -237,7 +248,7 @@ struct RowTile {
     static __device__ __forceinline__ int row_of(int i, int tid)
     {
         if (TRANS) return t_k4(tid) < Q ? 4 * t_r4(tid) + i : -1;
-        return i < NREG ? (i * 8 + (tid >> 5)) * RPU + (tid & 31) / Q : -1;
+        return i < NREG ? (i * NW + (tid >> 5)) * RPU + (tid & 31) / Q : -1;
     }
 };
 
@@ -283,8 +294,8 @@ __device__ __forceinline__ int float_key_tc(float f) { int i = __float_as_int(f)
 // Outputs: dsimT[tile][k][128] = d loss / d sim * (1 / |gt|) (zeros for padded rows / pixels), lmask[k / 32][pixel] =
 // label bits (sim == row max), and the loss partial sums.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KC, bool PLANAR>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int KC, bool PLANAR, int NT>                      // NT = 256 or 512 threads: NT / 128 column parts per pixel in the row pass
+__global__ void __launch_bounds__(NT, 1)
 k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_anneal, const float* __restrict__ gt,
          const uint8_t* __restrict__ wimg, const int* __restrict__ zarg, float* __restrict__ dsimT,
          uint32_t* __restrict__ lmask, int64_t Npad, SimStats* __restrict__ stats, int ns)
@@ -298,8 +309,10 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
     __shared__ __align__(8) uint64_t s_wfull[MAX_STAGES], s_mma[MAX_STAGES], s_acc;
     __shared__ uint32_t s_tmem;
     __shared__ float s_ss[128];
-    __shared__ float s_pv[2][128], s_ps[2][128], s_pw[2][128];
-    __shared__ int s_pi[2][128];
+    constexpr int NPARTS = NT / 128;
+    using XTile = RowTile<KC, PLANAR, NT / 32>;
+    __shared__ float s_pv[NPARTS][128], s_ps[NPARTS][128], s_pw[NPARTS][128];
+    __shared__ int s_pi[NPARTS][128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N0 = 16 * ((NP + 31) / 32), N1 = NP - N0;
     const bool want_lo = nterms == 3;
@@ -328,8 +341,8 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
 
     // Two register sets: the loads of chunk g + 2 go out right after chunk g has been written to shared memory, so a
     // load has a whole chunk period to land before it is consumed.
-    RowTile<KC, PLANAR> xa, xb;
-    auto load_x = [&](RowTile<KC, PLANAR>& xt, int64_t it2, int c2) {
+    XTile xa, xb;
+    auto load_x = [&](XTile& xt, int64_t it2, int c2) {
         // rows = pixels, reduction = codebook width; (it2, c2) may run past this tile: normalise
         it2 += c2 / nchunks;
         c2 %= nchunks;
@@ -371,7 +384,7 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
         // ---- 1 / |gt| of the tile's pixels
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int r = RowTile<KC, PLANAR>::row_of(i, tid);
+            const int r = XTile::row_of(i, tid);
             if (r >= 0) atomicAdd(&s_ss[r], ss[i]);
         }
         __syncthreads();
@@ -385,8 +398,8 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
 
         // ---- epilogue: the similarity row of pixel `row`, columns [cbeg, cend).  Everything is evaluated on the raw
         // accumulators r_k (sim_k = r_k / |gt|, a positive scale): a2_k = c2 (r_k - r_max) = log2(e) t (sim_k - sim_max).
-        const int C0 = min(NP, 32 * ((NP + 63) / 64));
-        const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
+        const int NB = (NP + 31) / 32;                      // 32-column blocks; part p owns blocks [NB p / NPARTS, NB (p + 1) / NPARTS)
+        const int cbeg = 32 * (NB * part / NPARTS), cend = min(NP, 32 * (NB * (part + 1) / NPARTS));
         const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         // pass 1: row maximum, its first index, and the accumulator of column k^ (two chains: even / odd columns)
@@ -417,9 +430,11 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
         s_pv[part][row] = bv0;
         s_pi[part][row] = bi0;
         __syncthreads();
-        const float v0 = s_pv[0][row], v1 = s_pv[1][row];
-        const float rmax = v1 > v0 ? v1 : v0;
-        const int sarg = v1 > v0 ? s_pi[1][row] : s_pi[0][row];
+        float rmax = s_pv[0][row];
+        int sarg = s_pi[0][row];
+#pragma unroll
+        for (int q = 1; q < NPARTS; ++q)                    // ascending parts, strict >: the first maximum wins
+            if (s_pv[q][row] > rmax) { rmax = s_pv[q][row]; sarg = s_pi[q][row]; }
         const float c2 = LOG2E * t_anneal * inv;
         // pass 2: sum 2^a2 and sum 2^a2 a2
         float asum0 = 0.f, asum1 = 0.f, wsum0 = 0.f, wsum1 = 0.f;
@@ -444,8 +459,10 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
         s_ps[part][row] = asum0 + asum1;
         s_pw[part][row] = wsum0 + wsum1;
         __syncthreads();
-        const float asum = s_ps[0][row] + s_ps[1][row];
-        const float wsum = LN2 * (s_pw[0][row] + s_pw[1][row]);
+        float asum = 0.f, wsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPARTS; ++q) { asum += s_ps[q][row]; wsum += s_pw[q][row]; }
+        wsum *= LN2;
         const float ainv = 1.f / asum, logZ = __logf(asum);
         const float E = wsum * ainv - logZ;                 // sum P log P,  P = softmax(t sim)
         // pass 3: d loss / d sim_k * (1 / |gt|) = kd 2^a2 (ln2 a2 - (logZ + E)) (+ the two one-hot terms below), label bits
