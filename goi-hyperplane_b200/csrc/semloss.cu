@@ -478,7 +478,8 @@ cudaError_t launch_sim(const goi_semloss_args& a, const Workspace& w, const Geom
 template <int KC, bool PLANAR>
 cudaError_t launch_dlut_t(const goi_semloss_args& a, const Workspace& w, const Geometry& g, cudaStream_t st)
 {
-    auto kern = tc5::k_dlut_tc<KC, PLANAR>;
+    constexpr int NT = 512;
+    auto kern = tc5::k_dlut_tc<KC, PLANAR, NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     const int sms = device_sms();
@@ -486,7 +487,7 @@ cudaError_t launch_dlut_t(const goi_semloss_args& a, const Workspace& w, const G
     int64_t n_ranges = sms / n_slices;                          // CTAs of one pixel range sit next to each other: they
     if (n_ranges < 1) n_ranges = 1;                             // read the same dsimT tiles at about the same time (L2)
     if (n_ranges > g.ntiles) n_ranges = g.ntiles;
-    kern<<<(unsigned)(n_ranges * n_slices), tc5::THREADS, g.smem, st>>>(a.N, a.D, a.K, g.NP, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
+    kern<<<(unsigned)(n_ranges * n_slices), NT, g.smem, st>>>(a.N, a.D, a.K, g.NP, a.precision == GOI_SEMLOSS_TF32 ? 1 : 3,
                                                                        n_slices, a.gt, w.dsimT, w.dlut1, g.ns);
     return cudaGetLastError();
 }

@@ -530,14 +530,15 @@ k_sim_tc(int64_t N, int D, int K, int NP, int nchunks, int nterms, float t_annea
 // width columns, every n_ranges-th pixel tile).  A operand = the gt slice (rows = d, reduction = pixels), B operand =
 // dsimT (rows = codebook rows, reduction = pixels), accumulators [128 x NP] fp32 in TMEM for the whole kernel.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KC, bool PLANAR>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int KC, bool PLANAR, int NT>                      // NT = 256 or 512 threads
+__global__ void __launch_bounds__(NT, 1)
 k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float* __restrict__ gt,
           const float* __restrict__ dsimT, float* __restrict__ dlut1, int ns)
 {
     constexpr int Q = KC / 4, RPU = 32 / Q;                 // pieces per row; rows per warp instruction
     constexpr int CPT = 128 / KC;                           // chunks per pixel tile
-    constexpr int BIT = KC == 32 ? 10 : 8;                  // B-operand pieces per thread: ceil(NP / RPU / 8), NP <= 304 | 512
+    constexpr int NW = NT / 32;                             // warps
+    constexpr int BIT = ((KC == 32 ? 76 : 64) + NW - 1) / NW;      // B-operand pieces per thread: ceil(NP / RPU / NW), NP <= 304 | 512
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int bbytes = NP * row_bytes(KC);
@@ -574,7 +575,7 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
 
     // PLANAR: gt[d][pixel] is contiguous along the reduction (pixels) -> direct; row-major gt[pixel][d] -> transposed.
     // Two register sets, loads two chunks ahead (see k_sim_tc).
-    struct Regs { RowTile<KC, !PLANAR> at; float4 bv[BIT]; };
+    struct Regs { RowTile<KC, !PLANAR, NW> at; float4 bv[BIT]; };
     Regs ra, rb;
     auto load_ab = [&](Regs& rg, int64_t ch) {
         if (ch >= my_chunks) return;
@@ -584,7 +585,7 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
         const float* bsrc = dsimT + (size_t)tile * NP * 128 + (ch % CPT) * KC;
 #pragma unroll
         for (int i = 0; i < BIT; ++i) {
-            const int u = i * 8 + warp;
+            const int u = i * NW + warp;
             const int r = u * RPU + lane / Q, k4 = lane % Q;    // a warp instruction reads whole 128-byte (64-byte) rows
             if (u < b_units) rg.bv[i] = __ldg(reinterpret_cast<const float4*>(bsrc + (size_t)r * 128 + 4 * k4));
         }
@@ -602,7 +603,7 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
         rg.at.store(a_hi, a_lo, want_lo, tid, ss_unused);
 #pragma unroll
         for (int i = 0; i < BIT; ++i) {
-            const int uu = i * 8 + warp;
+            const int uu = i * NW + warp;
             const int r = uu * RPU + lane / Q, k4 = lane % Q;
             if (uu < b_units)
                 store_split(b_hi, b_lo, (uint32_t)piece_off(KC, r, k4), rg.bv[i].x, rg.bv[i].y, rg.bv[i].z, rg.bv[i].w, want_lo);
@@ -625,9 +626,10 @@ k_dlut_tc(int64_t N, int D, int K, int NP, int nterms, int n_slices, const float
     if (my_chunks > 0) {
         wait(smem_u32(&s_acc), 0);
         asm volatile("tcgen05.fence::after_thread_sync;");
+        constexpr int NPARTS = NT / 128;
         const int row = tid & 127, part = tid >> 7;
-        const int C0 = min(NP, 32 * ((NP + 63) / 64));
-        const int cbeg = part ? C0 : 0, cend = part ? NP : C0;
+        const int NB = (NP + 31) / 32;
+        const int cbeg = 32 * (NB * part / NPARTS), cend = min(NP, 32 * (NB * (part + 1) / NPARTS));
         const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         const bool dv = d0 + row < D;
         float* const out = dlut1 + d0 + row;
