@@ -185,6 +185,59 @@ def test_cuda_planar_ragged_sizes_match_oracle(N, S, K, D):
 
 
 @pytest.mark.gpu
+def test_cuda_matches_the_reference_chain_at_bench_width():
+    """At a size the CPU oracle cannot hold (400 k pixels, K = 300, D = 256 -- the bench's shape at a quarter of its
+    pixels) the comparator is the reference's own expression chain, train.py:142-163, run by torch on the same GPU in
+    fp32 (allow_tf32 off, like the reference): loss terms to 1e-5 relative, gradients to 1e-3 of the tensor's max."""
+    from torch.nn.functional import cosine_similarity, log_softmax, softmax
+    from goi_b200.semantic_loss import semantic_loss
+    H, Wd, S, K, D = 400, 1000, 16, 300, 256
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(11)
+    sem = torch.randn(S, H, Wd, generator=g).to(dev).requires_grad_(True)
+    Wm = (torch.randn(K, S, generator=g) * 0.4).to(dev).requires_grad_(True)
+    bm = (torch.randn(K, generator=g) * 0.1).to(dev).requires_grad_(True)
+    lut = (torch.randn(K, D, generator=g) * 0.5 + 0.1).to(dev).requires_grad_(True)
+    ape = (lut.detach()[torch.randint(0, K, (H * Wd,), generator=g).to(dev)] + 0.3 * torch.randn(H * Wd, D, device=dev)).t().reshape(D, H, Wd).contiguous()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sem_feature = sem.permute(1, 2, 0).reshape(-1, S)                                  # train.py:142
+        sem_label = softmax(torch.nn.functional.linear(sem_feature, Wm, bm), dim=-1)       # :143-144
+        gtl = ape.float().permute(1, 2, 0).reshape(-1, D)
+        gtl = gtl / gtl.norm(dim=1, keepdim=True)                                          # :147-148
+        lut1 = lut / lut.norm(dim=1, keepdim=True)                                         # :149
+        sim = gtl @ lut1.T                                                                 # :150
+        sim_val = sim.max(dim=1, keepdim=True)[0]
+        label = (sim == sim_val).float().detach()                                          # :152-153
+        lab = torch.nn.MSELoss()(sem_label, label) * 50                                    # :154
+        sl = 1 - sim_val.mean()                                                            # :155
+        recc = 1 - cosine_similarity(lut[sem_label.argmax(-1)], gtl, dim=-1).mean()        # :156
+        b = softmax(sim * 1, dim=1) * log_softmax(sim * 1, dim=1)                          # :157-159 (t = 1)
+        sl1 = -1.0 * b.sum(dim=-1).mean()                                                  # :160
+        ref_loss = lab + sl + 0.3 * sl1 + recc                                             # :163
+        ref_loss.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    ref = dict(loss=float(ref_loss.detach()), lab=float(lab.detach()), sl=float(sl.detach()), sl1=float(sl1.detach()), recc=float(recc.detach()),
+               d_sem_feature=sem.grad.clone(), d_mlp_weight=Wm.grad.clone(), d_mlp_bias=bm.grad.clone(), d_lut=lut.grad.clone())
+    del sim, label, b, sem_label, gtl
+    for t in (sem, Wm, bm, lut):
+        t.grad = None
+    torch.cuda.empty_cache()
+    loss, terms = semantic_loss(sem, (Wm, bm), lut, ape, iteration=1)
+    loss.backward()
+    tv = terms.cpu().numpy()
+    cu = dict(loss=tv[0], lab=tv[1], sl=tv[2], sl1=tv[3], recc=tv[4], d_sem_feature=sem.grad, d_mlp_weight=Wm.grad,
+              d_mlp_bias=bm.grad, d_lut=lut.grad)
+    for k in TERMS:
+        assert abs(float(cu[k]) - ref[k]) <= LOSS_RTOL * max(1.0, abs(ref[k])), (k, float(cu[k]), ref[k])
+    for k in GRADS:
+        d = float((cu[k] - ref[k]).abs().max() / ref[k].abs().max())
+        assert d <= GRAD_RTOL, (k, d)
+
+
+@pytest.mark.gpu
 def test_tf32_gemms_stay_close_and_scale_with_upstream_gradient():
     N, S, K, D = 20000, 16, 300, 256
     g = torch.Generator().manual_seed(5)
