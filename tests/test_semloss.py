@@ -238,6 +238,44 @@ def test_cuda_matches_the_reference_chain_at_bench_width():
 
 
 @pytest.mark.gpu
+def test_c_abi_optional_outputs_may_be_null():
+    """include/goi_semloss.h: dL_dx, dL_dmlp_weight (+ bias) and dL_dlut are optional.  Straight through the C ABI: a call
+    with only the losses wanted must return the same loss terms as the full call and must not touch anything else."""
+    from goi_b200 import semantic_loss as sl
+    L = sl.lib()
+    N, S, K, D = 3000, 16, 300, 256
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, S, generator=g).to(dev)
+    W, b = (torch.randn(K, S, generator=g) * 0.4).to(dev), (torch.randn(K, generator=g) * 0.1).to(dev)
+    lut = (torch.randn(K, D, generator=g) * 0.5 + 0.1).to(dev)
+    gt = torch.randn(N, D, generator=g).to(dev)
+    ws = torch.empty((L.goi_semloss_workspace_bytes(N, K, D),), dtype=torch.uint8, device=dev)
+
+    def call(want_dx, want_dw, want_dlut):
+        losses = torch.zeros(8, device=dev)
+        dx, dW, db, dl = torch.full_like(x, 7.0), torch.full_like(W, 7.0), torch.full_like(b, 7.0), torch.full_like(lut, 7.0)
+        a = sl.goi_semloss_args(N, S, K, D, 0, 1.0, 0, x.data_ptr(), S, 1, gt.data_ptr(), 0, 0, W.data_ptr(), b.data_ptr(),
+                                lut.data_ptr(), ws.data_ptr(), ws.numel(), losses.data_ptr(),
+                                dx.data_ptr() if want_dx else None, dW.data_ptr() if want_dw else None,
+                                db.data_ptr() if want_dw else None, dl.data_ptr() if want_dlut else None)
+        rc = L.goi_semantic_loss(C.byref(a), torch.cuda.current_stream(dev).cuda_stream)
+        assert rc == 0, L.goi_semloss_last_error()
+        torch.cuda.synchronize()
+        return losses.cpu(), dx, dW, db, dl
+
+    full = call(True, True, True)
+    for flags in ((False, False, False), (True, False, False), (False, True, False), (False, False, True)):
+        part = call(*flags)
+        assert torch.allclose(part[0][:6], full[0][:6], rtol=1e-6, atol=1e-7), flags
+        for i, want in zip((1, 2, 3, 4), (flags[0], flags[1], flags[1], flags[2])):
+            if want:
+                assert rel(part[i].cpu().numpy(), full[i].cpu().numpy()) <= 1e-5, (flags, i)     # atomics: summation order
+            else:
+                assert bool((part[i] == 7.0).all()), (flags, i)                                  # untouched
+
+
+@pytest.mark.gpu
 def test_tf32_gemms_stay_close_and_scale_with_upstream_gradient():
     N, S, K, D = 20000, 16, 300, 256
     g = torch.Generator().manual_seed(5)
