@@ -169,7 +169,8 @@ def test_cuda_matches_oracle(N, S, K, D, it):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,S,K,D", [(4099, 16, 300, 256), (515, 7, 33, 10), (130, 32, 512, 64)])
+@pytest.mark.parametrize("N,S,K,D", [(4099, 16, 300, 256), (515, 7, 33, 10), (130, 32, 512, 64), (201, 1, 20, 40), (300, 16, 300, 512),
+                                     (259, 12, 320, 96)])
 def test_cuda_planar_ragged_sizes_match_oracle(N, S, K, D):
     """Planar [S,1,N] / [D,1,N] inputs whose pixel count is not a multiple of 4 (no 16-byte loads along the pixel axis),
     codebook widths that are not a multiple of the staged chunk, partial last tiles: the scalar-load and zero-padding
